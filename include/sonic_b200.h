@@ -1,0 +1,162 @@
+/* libsonic_b200 -- C ABI of the B200-native Sonic prover hot path.
+ *
+ * The reference (sdiehl/sonic, pure Haskell) has no FFI of its own; the boundary is
+ * defined by the Haskell functions whose bodies this library replaces.  Every entry
+ * point names the reference interface it stands in for (paths relative to the
+ * reference tree).  INTEGRATION.md shows the `foreign import ccall` side.
+ *
+ * Conventions
+ *   Fr  : 32 bytes, little-endian, canonical residue in [0, r)   (not Montgomery)
+ *   G1  : 48 bytes, compressed: big-endian x; bit7 = 1, bit6 = infinity,
+ *         bit5 = (y > (q-1)/2); infinity = 0xc0 || 0^47
+ *   Ownership: the caller owns all buffers; the library copies in and never keeps a
+ *   host pointer.  Handles are library-owned and immutable after creation.
+ *   Errors: 0 on success, a SONIC_ERR_* code otherwise; nothing is thrown across the
+ *   boundary.  sonic_last_error() returns, for the calling thread, the text the
+ *   reference would have passed to `panic` where there is one.
+ *   There is no CPU fallback: every call fails with SONIC_ERR_NO_DEVICE when no
+ *   CUDA device is usable.
+ */
+#ifndef SONIC_B200_H
+#define SONIC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SONIC_FR_BYTES 32
+#define SONIC_G1_BYTES 48
+#define SONIC_G1_RAW_BYTES 96 /* uncompressed affine: x || y, each 48-byte little-endian canonical; infinity = zeros */
+
+enum {
+    SONIC_OK = 0,
+    SONIC_ERR_INVALID_ARG = 1,
+    SONIC_ERR_SRS_TOO_SHORT = 2,  /* `index` panic, src/Sonic/CommitmentScheme.hs:70-73 */
+    SONIC_ERR_D_TOO_SMALL = 3,    /* `prove` guard, src/Sonic/Protocol.hs:54-55 */
+    SONIC_ERR_DIV_BY_ZERO = 4,    /* `recip 0`: x = 0 in SRS.new, or z = 0 with negative exponents */
+    SONIC_ERR_NONCANONICAL = 5,   /* an Fr encoding >= r */
+    SONIC_ERR_CUDA = 6,
+    SONIC_ERR_BUFFER_TOO_SMALL = 7,
+    SONIC_ERR_NO_DEVICE = 8,
+    SONIC_ERR_NOT_INITIALISED = 9
+};
+
+/* families of SRS bases, indexed by exponent k in [-d, d] */
+enum {
+    SONIC_FAMILY_PLAIN = 0, /* g^{x^k}:       gNegativeX / gPositiveX,            src/Sonic/SRS.hs:33-34 */
+    SONIC_FAMILY_ALPHA = 1  /* g^{alpha x^k}: gNegativeAlphaX / gPositiveAlphaX,  src/Sonic/SRS.hs:37-39; k = 0 absent */
+};
+
+typedef struct sonic_srs sonic_srs;
+typedef struct sonic_circuit sonic_circuit;
+
+/* Binds the calling process to one CUDA device (one process per GPU; multi-GPU runs
+ * launch one process per device and exchange partial sums, see sonic_msm_g1_partial).
+ * `devices`/`ndev`: ndev must be 1; devices[0] is the CUDA ordinal (NULL = device 0). */
+int sonic_init(const int* devices, int ndev);
+void sonic_shutdown(void);
+
+const char* sonic_strerror(int code);
+/* copies the calling thread's last error text (NUL-terminated) into buf; returns its length */
+size_t sonic_last_error(char* buf, size_t cap);
+
+/* SRS.new :: Int -> Fr -> Fr -> SRS   (src/Sonic/SRS.hs:27-43), G1 vectors only.
+ * Generates all 4d+1 G1 elements on the device by fixed-base batch multiplication and
+ * keeps them resident in HBM until sonic_srs_free. */
+int sonic_srs_new(uint64_t d, const uint8_t x[32], const uint8_t alpha[32], sonic_srs** out);
+void sonic_srs_free(sonic_srs* srs);
+uint64_t sonic_srs_d(const sonic_srs* srs); /* srsD, src/Sonic/SRS.hs:12 */
+
+/* Element of gNegativeX/gPositiveX/gNegativeAlphaX/gPositiveAlphaX by exponent
+ * (record fields, src/Sonic/SRS.hs:13-18).  family ALPHA, exponent 0 -> SONIC_ERR_SRS_TOO_SHORT. */
+int sonic_srs_g1(const sonic_srs* srs, int family, int64_t exponent, uint8_t out[48]);
+/* `count` consecutive elements starting at `exponent`, 48 bytes each */
+int sonic_srs_g1_range(const sonic_srs* srs, int family, int64_t exponent, uint64_t count, uint8_t* out);
+
+/* commitPoly :: SRS -> Int -> VLaurent Fr -> G1   (src/Sonic/CommitmentScheme.hs:20-33)
+ * f is given as a dense window: coeffs32[i] is the coefficient of X^(lo+i), i < len.
+ * Zero coefficients are what the sparse reference does not hold: they never index the SRS. */
+int sonic_commit(const sonic_srs* srs, int64_t max, int64_t lo, uint64_t len,
+                 const uint8_t* coeffs32, uint8_t out_g1[48]);
+
+/* openPoly :: SRS -> Fr -> VLaurent Fr -> (Fr, G1)   (src/Sonic/CommitmentScheme.hs:36-48) */
+int sonic_open(const sonic_srs* srs, const uint8_t z[32], int64_t lo, uint64_t len,
+               const uint8_t* coeffs32, uint8_t out_v[32], uint8_t out_w[48]);
+
+/* The fold inside commitPoly/openPoly as a standalone multi-scalar multiplication
+ * (src/Sonic/CommitmentScheme.hs:26-29,45-48): sum_i scalars[i] * base[family][lo+i]. */
+int sonic_msm_g1(const sonic_srs* srs, int family, int64_t lo, uint64_t len,
+                 const uint8_t* scalars32, uint8_t out[48]);
+/* Same, for one slice of a sharded MSM: the partial sum leaves as 96 raw bytes so that
+ * ranks can gather the partials (NCCL) and fold them with sonic_g1_sum. */
+int sonic_msm_g1_partial(const sonic_srs* srs, int family, int64_t lo, uint64_t len,
+                         const uint8_t* scalars32, uint8_t out_raw[96]);
+/* `<>` over n raw partial sums -> compressed G1 (src/Sonic/CommitmentScheme.hs:26,45) */
+int sonic_g1_sum(const uint8_t* raw96, uint64_t n, uint8_t out[48]);
+
+/* Scalars already resident in device memory (canonical little-endian, 32 bytes each);
+ * `d_scalars32` is a CUDA device pointer.  Used when the coefficient vectors are produced
+ * on the device, and by bench.py to time the path without host copies. */
+int sonic_msm_g1_device(const sonic_srs* srs, int family, int64_t lo, uint64_t len,
+                        const void* d_scalars32, uint8_t out[48]);
+
+/* ArithCircuit{weights = GateWeights{wL,wR,wO}, cs}  (src/Sonic/Protocol.hs:53; layout of
+ * src/Sonic/Constraints.hs:38-53): three dense Q x n row-major matrices of Fr and Q constants,
+ * kept resident across proofs. */
+int sonic_circuit_load(uint64_t n, uint64_t Q, const uint8_t* wL, const uint8_t* wR,
+                       const uint8_t* wO, const uint8_t* cs, sonic_circuit** out);
+void sonic_circuit_free(sonic_circuit* c);
+
+/* number of Fr values `prove` draws from MonadRandom: 2Q + 8, in the order
+ * c_{n+1..n+4}, y, z, ys[Q], zs[Q], u, v  (src/Sonic/Protocol.hs:58,66,76,84-85; Signature.hs:48,60) */
+uint64_t sonic_rnd_count(uint64_t Q);
+/* bytes of an encoded proof: (4Q+7) G1 + (2Q+5) Fr */
+uint64_t sonic_proof_size(uint64_t Q);
+
+/* prove :: SRS -> Assignment Fr -> ArithCircuit Fr -> m (Proof, RndOracle)
+ * (src/Sonic/Protocol.hs:47-109, with hscProve, src/Sonic/Signature.hs:32-72, inside).
+ * aL/aR/aO: n Fr each.  rnd: sonic_rnd_count(Q) Fr.  The proof is written in the field
+ * order of `Proof` / `HscProof` (Protocol.hs:28-38, Signature.hs:22-29):
+ *   prR prT prA prWa prB prWb prWt prS | Q x (S_j s_j W_j) | Q x (s'_j W'_j Q_j) | hscQv hscC hscU hscV */
+int sonic_prove(const sonic_srs* srs, const sonic_circuit* circuit, const uint8_t* aL,
+                const uint8_t* aR, const uint8_t* aO, const uint8_t* rnd, uint8_t* proof_out,
+                uint64_t cap, uint64_t* written);
+
+/* hscProve :: SRS -> BiVLaurent Fr -> [(Fr,Fr)] -> m HscProof   (src/Sonic/Signature.hs:32-72)
+ * s(X,Y) is the circuit's; yzs = m pairs (y_j, z_j) interleaved; uv = the two draws u, v.
+ * Output: Q x (S_j s_j W_j) | Q x (s'_j W'_j Q_j) | hscQv hscC hscU hscV. */
+int sonic_hsc_prove(const sonic_srs* srs, const sonic_circuit* circuit, uint64_t m,
+                    const uint8_t* yzs, const uint8_t* uv, uint8_t* out, uint64_t cap,
+                    uint64_t* written);
+
+/* ---- tuning and measurement hooks (not part of the reference surface) ---- */
+/* option names: "window_bits" (0 = automatic), "chunk" (0 = automatic) */
+int sonic_set_option(const char* name, int64_t value);
+/* device time in milliseconds of the kernels of the last call, by stage name; returns 0
+ * if unknown.  Stages: "msm", "msm.sort", "msm.accumulate", "msm.reduce", "poly", "total" */
+double sonic_last_timing_ms(const char* stage);
+/* number of kernel launches issued by this library since sonic_init */
+uint64_t sonic_launch_count(void);
+/* Register-only integer multiply-add microbenchmark: returns measured 32x32->64
+ * multiply-accumulates per second on the bound device (the roofline denominator). */
+double sonic_imad_peak_lmacs(int variant, int iters);
+/* Device self-tests of the arithmetic layer (raw Montgomery-form limbs, little-endian u32):
+ * field 0 = Fq (12 limbs), 1 = Fr (8 limbs); op 0 mul, 1 add, 2 sub, 3 to_mont, 4 from_mont,
+ * 5 inv, 6 sqr, 7 neg.  G1: points as XYZZ (48 limbs); op 0 acc+affine(b.x,b.y), 1 acc+b, 2 2*acc,
+ * 3 2*affine(a.x,a.y); outputs affine (24 limbs) and the compressed encoding. */
+int sonic_selftest_field(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out, uint32_t n);
+int sonic_selftest_g1(int op, const uint32_t* a_xyzz, const uint32_t* b_xyzz, uint32_t* out_affine,
+                      uint8_t* out_comp, uint32_t n);
+/* device memory helpers for harnesses that have no CUDA binding of their own */
+int sonic_dev_alloc(uint64_t bytes, void** out);
+int sonic_dev_free(void* p);
+int sonic_dev_upload(void* dst, const void* src, uint64_t bytes);
+int sonic_dev_download(void* dst, const void* src, uint64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SONIC_B200_H */

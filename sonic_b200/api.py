@@ -1,0 +1,302 @@
+"""Host-side mirror of the reference's prover interface, calling the CUDA library.
+
+Reference interfaces mirrored (paths relative to the reference tree):
+  SRS.new / record fields      src/Sonic/SRS.hs:11-43
+  commitPoly, openPoly         src/Sonic/CommitmentScheme.hs:20-48
+  prove, Proof, RndOracle      src/Sonic/Protocol.hs:28-109
+  hscProve, HscProof           src/Sonic/Signature.hs:22-72
+  ArithCircuit, Assignment, GateWeights   bulletproofs records used at Protocol.hs:17
+
+Values: Fr is a Python int in [0, r); a G1 element is its 48-byte compressed encoding
+(`bytes`); a `VLaurent Fr` is a dict {exponent: coefficient}.  Nothing here computes on
+the CPU beyond packing bytes: all field, curve and polynomial arithmetic happens on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_uint64, c_void_p
+from dataclasses import dataclass, field
+from typing import Dict, List, Sequence, Tuple
+
+from . import capi
+from .capi import FAMILY_ALPHA, FAMILY_PLAIN, SonicError, check, lib
+
+R_MODULUS = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+G1Bytes = bytes
+Laurent = Dict[int, int]
+
+
+def _fr(x: int) -> bytes:
+    return (x % R_MODULUS).to_bytes(32, "little")
+
+
+def _frs(xs: Sequence[int]) -> bytes:
+    return b"".join((x % R_MODULUS).to_bytes(32, "little") for x in xs)
+
+
+def _dense(f: Laurent) -> Tuple[int, int, bytes]:
+    """Sparse Laurent polynomial -> (lo, len, coefficient bytes); zero coefficients dropped
+    first, as the reference's normal form does."""
+    nz = {e: c % R_MODULUS for e, c in f.items() if c % R_MODULUS}
+    if not nz:
+        return 0, 0, b""
+    lo, hi = min(nz), max(nz)
+    zero = bytes(32)
+    return lo, hi - lo + 1, b"".join(_fr(nz[e]) if e in nz else zero for e in range(lo, hi + 1))
+
+
+@dataclass
+class GateWeights:
+    wL: List[List[int]]
+    wR: List[List[int]]
+    wO: List[List[int]]
+
+
+@dataclass
+class ArithCircuit:
+    weights: GateWeights
+    cs: List[int]
+    _handle: object = field(default=None, repr=False, compare=False)
+
+    def handle(self) -> "_Circuit":
+        if self._handle is None:
+            self._handle = _Circuit(self)
+        return self._handle
+
+
+@dataclass
+class Assignment:
+    aL: List[int]
+    aR: List[int]
+    aO: List[int]
+
+
+class _Circuit:
+    """Weights resident on the device across proofs (sonic_circuit_load)."""
+
+    def __init__(self, c: ArithCircuit):
+        capi.init()
+        w = c.weights
+        if not w.wL or not w.wL[0]:
+            raise SonicError(1, "Empty weights")
+        self.Q, self.n = len(w.wL), len(w.wL[0])
+        flat = lambda m: _frs([v for row in m for v in row])
+        h = c_void_p()
+        check(lib().sonic_circuit_load(self.n, self.Q, flat(w.wL), flat(w.wR), flat(w.wO), _frs(c.cs), ctypes.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().sonic_circuit_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class SRS:
+    """`SRS` record (src/Sonic/SRS.hs:11-22), G1 vectors resident in HBM behind a handle."""
+
+    def __init__(self, handle: c_void_p, d: int):
+        self._h = handle
+        self.srsD = d
+
+    @staticmethod
+    def new(d: int, x: int, alpha: int) -> "SRS":
+        """`SRS.new d x alpha` (src/Sonic/SRS.hs:27)."""
+        capi.init()
+        h = c_void_p()
+        check(lib().sonic_srs_new(d, _fr(x), _fr(alpha), ctypes.byref(h)))
+        return SRS(h, d)
+
+    def _range(self, family: int, lo: int, count: int) -> List[G1Bytes]:
+        out = ctypes.create_string_buffer(48 * count)
+        check(lib().sonic_srs_g1_range(self._h, family, lo, count, out))
+        raw = out.raw
+        return [raw[48 * i:48 * i + 48] for i in range(count)]
+
+    def g1(self, family: int, exponent: int) -> G1Bytes:
+        return self._range(family, exponent, 1)[0]
+
+    # the four G1 record fields, in the reference's index convention
+    @property
+    def gNegativeX(self) -> List[G1Bytes]:          # [i-1] = g^{x^-i}
+        return self._range(FAMILY_PLAIN, -self.srsD, self.srsD)[::-1]
+
+    @property
+    def gPositiveX(self) -> List[G1Bytes]:          # [i] = g^{x^i}
+        return self._range(FAMILY_PLAIN, 0, self.srsD + 1)
+
+    @property
+    def gNegativeAlphaX(self) -> List[G1Bytes]:     # [i-1] = g^{alpha x^-i}
+        return self._range(FAMILY_ALPHA, -self.srsD, self.srsD)[::-1]
+
+    @property
+    def gPositiveAlphaX(self) -> List[G1Bytes]:     # [i-1] = g^{alpha x^i}
+        return self._range(FAMILY_ALPHA, 1, self.srsD)
+
+    def free(self) -> None:
+        if self._h:
+            lib().sonic_srs_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def commitPoly(srs: SRS, maxm: int, fX: Laurent) -> G1Bytes:
+    """`commitPoly srs max f` (src/Sonic/CommitmentScheme.hs:20-33)."""
+    lo, ln, coeffs = _dense(fX)
+    out = ctypes.create_string_buffer(48)
+    check(lib().sonic_commit(srs._h, maxm, lo, ln, coeffs, out))
+    return out.raw
+
+
+def openPoly(srs: SRS, z: int, fX: Laurent) -> Tuple[int, G1Bytes]:
+    """`openPoly srs z f` (src/Sonic/CommitmentScheme.hs:36-48) -> (f(z), W)."""
+    lo, ln, coeffs = _dense(fX)
+    v = ctypes.create_string_buffer(32)
+    w = ctypes.create_string_buffer(48)
+    check(lib().sonic_open(srs._h, _fr(z), lo, ln, coeffs, v, w))
+    return int.from_bytes(v.raw, "little"), w.raw
+
+
+def msm(srs: SRS, family: int, lo: int, scalars) -> G1Bytes:
+    """sum_i scalars[i] * base[family][lo+i]: the fold of CommitmentScheme.hs:26-29 on its own.
+    `scalars`: list of ints, or a bytes / numpy buffer of 32-byte little-endian values."""
+    if isinstance(scalars, (list, tuple)):
+        n, data = len(scalars), _frs(scalars)
+    else:
+        data = scalars
+        n = (len(scalars) if isinstance(scalars, (bytes, bytearray)) else scalars.nbytes) // 32
+    out = ctypes.create_string_buffer(48)
+    check(lib().sonic_msm_g1(srs._h, family, lo, n, capi.buf(data) if not isinstance(data, bytes) else data, out))
+    return out.raw
+
+
+def msm_partial(srs: SRS, family: int, lo: int, scalars) -> bytes:
+    """One slice of a sharded MSM -> 96 raw bytes (see `g1_sum`)."""
+    if isinstance(scalars, (list, tuple)):
+        n, data = len(scalars), _frs(scalars)
+    else:
+        data = scalars
+        n = (len(scalars) if isinstance(scalars, (bytes, bytearray)) else scalars.nbytes) // 32
+    out = ctypes.create_string_buffer(96)
+    check(lib().sonic_msm_g1_partial(srs._h, family, lo, n, capi.buf(data) if not isinstance(data, bytes) else data, out))
+    return out.raw
+
+
+def g1_sum(raw_partials: Sequence[bytes]) -> G1Bytes:
+    """`<>` over the partial sums gathered from the ranks."""
+    capi.init()
+    out = ctypes.create_string_buffer(48)
+    data = b"".join(raw_partials)
+    check(lib().sonic_g1_sum(data, len(raw_partials), out))
+    return out.raw
+
+
+@dataclass
+class HscProof:
+    """src/Sonic/Signature.hs:22-29."""
+    hscS: List[Tuple[G1Bytes, Tuple[int, G1Bytes]]]
+    hscW: List[Tuple[int, G1Bytes, G1Bytes]]
+    hscQv: G1Bytes
+    hscC: G1Bytes
+    hscU: int
+    hscV: int
+
+
+@dataclass
+class Proof:
+    """src/Sonic/Protocol.hs:28-38."""
+    prR: G1Bytes
+    prT: G1Bytes
+    prA: int
+    prWa: G1Bytes
+    prB: int
+    prWb: G1Bytes
+    prWt: G1Bytes
+    prS: int
+    prHscProof: HscProof
+
+
+@dataclass
+class RndOracle:
+    """src/Sonic/Protocol.hs:41-45."""
+    rndOracleY: int
+    rndOracleZ: int
+    rndOracleYZs: List[Tuple[int, int]]
+
+
+def _parse_hsc(buf: bytes, m: int, pos: int = 0) -> HscProof:
+    def G():
+        nonlocal pos
+        v = buf[pos:pos + 48]
+        pos += 48
+        return v
+
+    def F():
+        nonlocal pos
+        v = int.from_bytes(buf[pos:pos + 32], "little")
+        pos += 32
+        return v
+
+    hscS = []
+    for _ in range(m):
+        cm = G(); s = F(); w = G()
+        hscS.append((cm, (s, w)))
+    hscW = []
+    for _ in range(m):
+        sp = F(); wp = G(); qj = G()
+        hscW.append((sp, wp, qj))
+    qv = G(); c = G(); u = F(); v = F()
+    return HscProof(hscS, hscW, qv, c, u, v)
+
+
+def parse_proof(buf: bytes, Q: int) -> Proof:
+    G = lambda o: buf[o:o + 48]
+    F = lambda o: int.from_bytes(buf[o:o + 32], "little")
+    return Proof(prR=G(0), prT=G(48), prA=F(96), prWa=G(128), prB=F(176), prWb=G(208), prWt=G(256),
+                 prS=F(304), prHscProof=_parse_hsc(buf, Q, 336))
+
+
+def prove_bytes(srs: SRS, assignment: Assignment, circuit: ArithCircuit, rnd: Sequence[int]) -> bytes:
+    """The boundary call itself: one `sonic_prove`, proof bytes in record order."""
+    ch = circuit.handle()
+    n, Q = ch.n, ch.Q
+    if not (len(assignment.aL) == len(assignment.aR) == len(assignment.aO) == n):
+        raise SonicError(1, "assignment length differs from the circuit's n")
+    if len(rnd) != 2 * Q + 8:
+        raise SonicError(1, "prove draws 2Q+8 random field elements")
+    size = int(lib().sonic_proof_size(Q))
+    out = ctypes.create_string_buffer(size)
+    written = c_uint64(0)
+    check(lib().sonic_prove(srs._h, ch.h, _frs(assignment.aL), _frs(assignment.aR), _frs(assignment.aO),
+                            _frs(rnd), out, size, ctypes.byref(written)))
+    return out.raw[:written.value]
+
+
+def prove(srs: SRS, assignment: Assignment, circuit: ArithCircuit, rnd: Sequence[int]) -> Tuple[Proof, RndOracle]:
+    """`prove srs assignment circuit` (src/Sonic/Protocol.hs:47-109).  `rnd` supplies the
+    MonadRandom draws in the reference's order: c_{n+1..n+4}, y, z, ys[Q], zs[Q], u, v."""
+    buf = prove_bytes(srs, assignment, circuit, rnd)
+    Q = circuit.handle().Q
+    rnd = [r % R_MODULUS for r in rnd]
+    oracle = RndOracle(rnd[4], rnd[5], list(zip(rnd[6:6 + Q], rnd[6 + Q:6 + 2 * Q])))
+    return parse_proof(buf, Q), oracle
+
+
+def hscProve(srs: SRS, circuit: ArithCircuit, yzs: Sequence[Tuple[int, int]], u: int, v: int) -> HscProof:
+    """`hscProve srs sXY yzs` (src/Sonic/Signature.hs:32-72); s(X,Y) is the circuit's
+    (`sPoly weights`), `u` and `v` are its two `rnd` draws."""
+    ch = circuit.handle()
+    m = len(yzs)
+    size = (4 * m + 2) * 48 + (2 * m + 2) * 32
+    out = ctypes.create_string_buffer(size)
+    written = c_uint64(0)
+    flat = _frs([x for pair in yzs for x in pair])
+    check(lib().sonic_hsc_prove(srs._h, ch.h, m, flat, _frs([u, v]), out, size, ctypes.byref(written)))
+    return _parse_hsc(out.raw, m)

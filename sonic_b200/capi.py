@@ -1,0 +1,137 @@
+"""ctypes binding of include/sonic_b200.h (the same symbols a `foreign import ccall` binds)."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_size_t, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsonic_b200.so")
+
+SONIC_OK = 0
+ERR_NAMES = {
+    1: "INVALID_ARG", 2: "SRS_TOO_SHORT", 3: "D_TOO_SMALL", 4: "DIV_BY_ZERO", 5: "NONCANONICAL",
+    6: "CUDA", 7: "BUFFER_TOO_SMALL", 8: "NO_DEVICE", 9: "NOT_INITIALISED",
+}
+FAMILY_PLAIN, FAMILY_ALPHA = 0, 1
+
+
+class SonicError(RuntimeError):
+    """A non-zero status from the C ABI; `.text` is what the reference passes to `panic`."""
+
+    def __init__(self, code: int, text: str):
+        self.code = code
+        self.kind = ERR_NAMES.get(code, str(code))
+        self.text = text
+        super().__init__(f"[{self.kind}] {text}")
+
+
+_lib = None
+_ready = False
+
+# every symbol include/sonic_b200.h declares: name -> (restype, argtypes)
+_u8p = c_void_p
+SYMBOLS = {
+    "sonic_init": (c_int, [POINTER(c_int), c_int]),
+    "sonic_shutdown": (None, []),
+    "sonic_strerror": (c_char_p, [c_int]),
+    "sonic_last_error": (c_size_t, [ctypes.c_char_p, c_size_t]),
+    "sonic_srs_new": (c_int, [c_uint64, _u8p, _u8p, POINTER(c_void_p)]),
+    "sonic_srs_free": (None, [c_void_p]),
+    "sonic_srs_d": (c_uint64, [c_void_p]),
+    "sonic_srs_g1": (c_int, [c_void_p, c_int, c_int64, _u8p]),
+    "sonic_srs_g1_range": (c_int, [c_void_p, c_int, c_int64, c_uint64, _u8p]),
+    "sonic_commit": (c_int, [c_void_p, c_int64, c_int64, c_uint64, _u8p, _u8p]),
+    "sonic_open": (c_int, [c_void_p, _u8p, c_int64, c_uint64, _u8p, _u8p, _u8p]),
+    "sonic_msm_g1": (c_int, [c_void_p, c_int, c_int64, c_uint64, _u8p, _u8p]),
+    "sonic_msm_g1_partial": (c_int, [c_void_p, c_int, c_int64, c_uint64, _u8p, _u8p]),
+    "sonic_g1_sum": (c_int, [_u8p, c_uint64, _u8p]),
+    "sonic_msm_g1_device": (c_int, [c_void_p, c_int, c_int64, c_uint64, c_void_p, _u8p]),
+    "sonic_circuit_load": (c_int, [c_uint64, c_uint64, _u8p, _u8p, _u8p, _u8p, POINTER(c_void_p)]),
+    "sonic_circuit_free": (None, [c_void_p]),
+    "sonic_rnd_count": (c_uint64, [c_uint64]),
+    "sonic_proof_size": (c_uint64, [c_uint64]),
+    "sonic_prove": (c_int, [c_void_p, c_void_p, _u8p, _u8p, _u8p, _u8p, _u8p, c_uint64, POINTER(c_uint64)]),
+    "sonic_hsc_prove": (c_int, [c_void_p, c_void_p, c_uint64, _u8p, _u8p, _u8p, c_uint64, POINTER(c_uint64)]),
+    "sonic_set_option": (c_int, [c_char_p, c_int64]),
+    "sonic_last_timing_ms": (c_double, [c_char_p]),
+    "sonic_launch_count": (c_uint64, []),
+    "sonic_imad_peak_lmacs": (c_double, [c_int, c_int]),
+    "sonic_selftest_field": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, ctypes.c_uint32]),
+    "sonic_selftest_g1": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_uint32]),
+    "sonic_dev_alloc": (c_int, [c_uint64, POINTER(c_void_p)]),
+    "sonic_dev_free": (c_int, [c_void_p]),
+    "sonic_dev_upload": (c_int, [c_void_p, c_void_p, c_uint64]),
+    "sonic_dev_download": (c_int, [c_void_p, c_void_p, c_uint64]),
+}
+
+
+def lib():
+    """Loads libsonic_b200.so; raises (loudly) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SonicError(8, f"{LIB_PATH} is missing: build it with `make` / `__graft_entry__.build()`; "
+                                "there is no CPU fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    buf = ctypes.create_string_buffer(1024)
+    lib().sonic_last_error(buf, 1024)
+    return buf.value.decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    if rc != SONIC_OK:
+        raise SonicError(rc, last_error())
+
+
+def init(device: int | None = None) -> None:
+    """Binds this process to one GPU (LOCAL_RANK under torchrun, else device 0)."""
+    global _ready
+    if _ready:
+        return
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = (c_int * 1)(device)
+    check(lib().sonic_init(dev, 1))
+    _ready = True
+
+
+def shutdown() -> None:
+    global _ready
+    if _ready:
+        lib().sonic_shutdown()
+        _ready = False
+
+
+def set_option(name: str, value: int) -> None:
+    check(lib().sonic_set_option(name.encode(), value))
+
+
+def last_timing_ms(stage: str = "total") -> float:
+    return float(lib().sonic_last_timing_ms(stage.encode()))
+
+
+def launch_count() -> int:
+    return int(lib().sonic_launch_count())
+
+
+def buf(b) -> c_void_p:
+    """Pointer to a bytes-like / numpy / ctypes buffer without copying."""
+    if b is None:
+        return c_void_p(0)
+    if isinstance(b, (bytes, bytearray)):
+        return ctypes.cast(ctypes.c_char_p(bytes(b)) if isinstance(b, bytes) else (ctypes.c_char * len(b)).from_buffer(b), c_void_p)
+    if hasattr(b, "ctypes"):  # numpy
+        return c_void_p(b.ctypes.data)
+    if hasattr(b, "data_ptr"):  # torch
+        return c_void_p(b.data_ptr())
+    return ctypes.cast(b, c_void_p)

@@ -1,0 +1,178 @@
+// BLS12-381 G1 group law in extended Jacobian ("XYZZ") coordinates.
+//
+// Replaces (by value) the elliptic-curve package's `<>`, `mul`, `mempty` on
+// `G1 BLS12381` used at src/Sonic/CommitmentScheme.hs:26-29,45-48 and
+// src/Sonic/SRS.hs:33-39 of the reference.  Results are only ever compared /
+// exported in canonical affine form, so the internal representation is free.
+//
+// XYZZ: x = X/ZZ, y = Y/ZZZ with ZZ^3 = ZZZ^2; infinity <=> ZZ == 0.
+// Affine table entries use (0,0) for infinity ((0,0) is not on y^2 = x^3 + 4).
+// Formulas: EFD madd-2008-s (8M+2S), add-2008-s (12M+2S), dbl-2008-s-1, mdbl-2008-s-1.
+#pragma once
+#include "field.cuh"
+
+namespace sonic {
+
+struct G1Affine {
+    Fq x, y;
+    SONIC_HD bool is_inf() const {
+        uint32_t t = 0;
+        for (int i = 0; i < Fq::N; ++i) t |= x.l[i] | y.l[i];
+        return t == 0;
+    }
+    static SONIC_HD G1Affine inf() { G1Affine p; p.x = Fq::zero(); p.y = Fq::zero(); return p; }
+    static SONIC_HD G1Affine gen() {
+        G1Affine p;
+        for (int i = 0; i < Fq::N; ++i) { p.x.l[i] = FqParams::GX_M(i); p.y.l[i] = FqParams::GY_M(i); }
+        return p;
+    }
+};
+
+struct G1XYZZ {
+    Fq x, y, zz, zzz;
+    SONIC_HD bool is_inf() const { return zz.is_zero(); }
+    static SONIC_HD G1XYZZ inf() {
+        G1XYZZ p; p.x = Fq::one(); p.y = Fq::one(); p.zz = Fq::zero(); p.zzz = Fq::zero(); return p;
+    }
+    static SONIC_HD G1XYZZ from_affine(const G1Affine& a) {
+        if (a.is_inf()) return inf();
+        G1XYZZ p; p.x = a.x; p.y = a.y; p.zz = Fq::one(); p.zzz = Fq::one(); return p;
+    }
+};
+
+SONIC_HD G1Affine g1_neg(const G1Affine& a) {
+    G1Affine r; r.x = a.x; r.y = a.y.is_zero() ? a.y : fp_neg(a.y); return r;
+}
+
+// 2*(affine point)
+SONIC_HD G1XYZZ g1_mdbl(const G1Affine& a) {
+    if (a.is_inf()) return G1XYZZ::inf();
+    Fq U = fp_dbl(a.y);
+    Fq V = fp_sqr(U);
+    Fq W = fp_mul(U, V);
+    Fq S = fp_mul(a.x, V);
+    Fq X2 = fp_sqr(a.x);
+    Fq M = fp_add(fp_dbl(X2), X2);
+    G1XYZZ r;
+    r.x = fp_sub(fp_sqr(M), fp_dbl(S));
+    r.y = fp_sub(fp_mul(M, fp_sub(S, r.x)), fp_mul(W, a.y));
+    r.zz = V;
+    r.zzz = W;
+    return r;
+}
+
+SONIC_HD G1XYZZ g1_dbl(const G1XYZZ& p) {
+    // infinity stays infinity: ZZ3 = V*ZZ1 = 0
+    Fq U = fp_dbl(p.y);
+    Fq V = fp_sqr(U);
+    Fq W = fp_mul(U, V);
+    Fq S = fp_mul(p.x, V);
+    Fq X2 = fp_sqr(p.x);
+    Fq M = fp_add(fp_dbl(X2), X2);
+    G1XYZZ r;
+    r.x = fp_sub(fp_sqr(M), fp_dbl(S));
+    r.y = fp_sub(fp_mul(M, fp_sub(S, r.x)), fp_mul(W, p.y));
+    r.zz = fp_mul(V, p.zz);
+    r.zzz = fp_mul(W, p.zzz);
+    return r;
+}
+
+// acc += a   (mixed addition; all exceptional cases handled, reference bench uses x = 1
+// so P + P and P + (-P) really occur: bench/Main.hs:23)
+SONIC_HD void g1_madd(G1XYZZ& acc, const G1Affine& a) {
+    if (a.is_inf()) return;
+    if (acc.is_inf()) { acc = G1XYZZ::from_affine(a); return; }
+    Fq U2 = fp_mul(a.x, acc.zz);
+    Fq S2 = fp_mul(a.y, acc.zzz);
+    Fq P = fp_sub(U2, acc.x);
+    Fq R = fp_sub(S2, acc.y);
+    if (P.is_zero()) {
+        if (R.is_zero()) acc = g1_mdbl(a);
+        else acc = G1XYZZ::inf();
+        return;
+    }
+    Fq PP = fp_sqr(P);
+    Fq PPP = fp_mul(P, PP);
+    Fq Q = fp_mul(acc.x, PP);
+    Fq X3 = fp_sub(fp_sub(fp_sqr(R), PPP), fp_dbl(Q));
+    Fq Y3 = fp_sub(fp_mul(R, fp_sub(Q, X3)), fp_mul(acc.y, PPP));
+    acc.x = X3;
+    acc.y = Y3;
+    acc.zz = fp_mul(acc.zz, PP);
+    acc.zzz = fp_mul(acc.zzz, PPP);
+}
+
+// acc += b   (full addition)
+SONIC_HD void g1_add(G1XYZZ& acc, const G1XYZZ& b) {
+    if (b.is_inf()) return;
+    if (acc.is_inf()) { acc = b; return; }
+    Fq U1 = fp_mul(acc.x, b.zz);
+    Fq U2 = fp_mul(b.x, acc.zz);
+    Fq S1 = fp_mul(acc.y, b.zzz);
+    Fq S2 = fp_mul(b.y, acc.zzz);
+    Fq P = fp_sub(U2, U1);
+    Fq R = fp_sub(S2, S1);
+    if (P.is_zero()) {
+        if (R.is_zero()) acc = g1_dbl(acc);
+        else acc = G1XYZZ::inf();
+        return;
+    }
+    Fq PP = fp_sqr(P);
+    Fq PPP = fp_mul(P, PP);
+    Fq Q = fp_mul(U1, PP);
+    Fq X3 = fp_sub(fp_sub(fp_sqr(R), PPP), fp_dbl(Q));
+    Fq Y3 = fp_sub(fp_mul(R, fp_sub(Q, X3)), fp_mul(S1, PPP));
+    acc.x = X3;
+    acc.y = Y3;
+    acc.zz = fp_mul(fp_mul(acc.zz, b.zz), PP);
+    acc.zzz = fp_mul(fp_mul(acc.zzz, b.zzz), PPP);
+}
+
+SONIC_HD G1XYZZ g1_neg_xyzz(const G1XYZZ& p) {
+    G1XYZZ r = p; r.y = p.y.is_zero() ? p.y : fp_neg(p.y); return r;
+}
+
+// canonical affine form (one field inversion)
+SONIC_HD G1Affine g1_to_affine(const G1XYZZ& p) {
+    if (p.is_inf()) return G1Affine::inf();
+    Fq zi = fp_inv(p.zzz);                 // 1/ZZZ
+    Fq t = fp_mul(p.zz, zi);               // ZZ/ZZZ = 1/Z
+    Fq zzi = fp_sqr(t);                    // 1/ZZ
+    G1Affine r;
+    r.x = fp_mul(p.x, zzi);
+    r.y = fp_mul(p.y, zi);
+    return r;
+}
+
+// k * p for a small unsigned multiplier (double-and-add, MSB first)
+SONIC_HD G1XYZZ g1_mul_small(const G1XYZZ& p, uint32_t k) {
+    G1XYZZ r = G1XYZZ::inf();
+    for (int b = 31; b >= 0; --b) {
+        r = g1_dbl(r);
+        if ((k >> b) & 1) g1_add(r, p);
+    }
+    return r;
+}
+
+// 48-byte compressed boundary encoding: big-endian x, flag bits
+// 0x80 compressed, 0x40 infinity, 0x20 y > (q-1)/2.  Input is canonical affine in Montgomery form.
+SONIC_HD void g1_compress(const G1Affine& a, uint8_t out[48]) {
+    if (a.is_inf()) {
+        out[0] = 0xC0;
+        for (int i = 1; i < 48; ++i) out[i] = 0;
+        return;
+    }
+    Fq xc = fp_from_mont(a.x);
+    Fq yc = fp_from_mont(a.y);
+    for (int i = 0; i < 12; ++i) {
+        uint32_t w = xc.l[11 - i];
+        out[4 * i + 0] = (uint8_t)(w >> 24);
+        out[4 * i + 1] = (uint8_t)(w >> 16);
+        out[4 * i + 2] = (uint8_t)(w >> 8);
+        out[4 * i + 3] = (uint8_t)(w);
+    }
+    out[0] |= 0x80;
+    if (fp_canonical_gt_half(yc)) out[0] |= 0x20;
+}
+
+}  // namespace sonic

@@ -1,0 +1,396 @@
+// Batched signed-digit Pippenger MSM over resident SRS bases.
+//
+// Stands in for the reference's commitment fold, one full scalar multiplication plus one
+// point addition per term (src/Sonic/CommitmentScheme.hs:26-29 and :45-48).  The value
+// is the same group element; only the summation order differs, and the group is abelian.
+//
+// A launch handles a batch of M independent MSMs ("jobs"): all 4Q+7 commitments and
+// openings of one proof go through the pipeline together so that every stage fills the
+// 148 SMs even though a single job has only 2e5-5e5 terms.
+//
+// Stages (all on one stream):
+//   1. digits+count : one thread per term recodes the scalar into W = ceil(255/c) signed
+//                     digits and histograms the global bucket ids (job, window, |digit|-1).
+//   2. scan         : exclusive prefix sum of the histogram -> bucket offsets.
+//   3. scatter      : same recode, atomic cursor per bucket -> entries sorted by bucket
+//                     (entry = point id | sign bit).
+//   4. accumulate   : the hot kernel.  The sorted entry list is cut into equal chunks of L
+//                     entries, one thread per chunk, so every lane of a warp performs the
+//                     same number of mixed additions regardless of how skewed the digit
+//                     histogram is.  Buckets that lie inside one chunk are written directly;
+//                     pieces of buckets that straddle chunk borders go to head/tail slots.
+//   5. fix-up       : one thread per straddling bucket folds its pieces; buckets with more
+//                     than HEAVY pieces (skewed scalars: zeros, +-1) are folded by a whole
+//                     block each.
+//   6. bucket reduce: sum_b (b+1) * B_b per window by segmented running sums + block tree.
+//   7. finish       : per job, Horner over the windows, one inversion, affine + compressed.
+#include "internal.h"
+#include "g1io.cuh"
+#include "scalar.cuh"
+
+namespace sonic {
+
+// ---- stage 1 / 3: digits -> histogram or scatter ----------------------------------------
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__ scalars, MsmJobTable tab,
+                                                    uint32_t n_tot, int c, int W, uint32_t B,
+                                                    uint32_t* __restrict__ counters,
+                                                    uint32_t* __restrict__ entries) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tot) return;
+    int j = 0;
+    while (j + 1 < tab.M && tab.prefix[j + 1] <= t) ++j;
+    const uint32_t local = t - tab.prefix[j];
+    const uint4* sp = reinterpret_cast<const uint4*>(scalars + (size_t)(tab.job[j].scalar_off + local) * 8);
+    uint4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+    uint32_t s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) return;
+    ScalarDigits sd(s, c);
+    const uint32_t pid = tab.job[j].point_base + local;
+    uint32_t gb0 = (uint32_t)j * (uint32_t)W * B;
+    for (int w = 0; w < W; ++w, gb0 += B) {
+        int32_t d = sd.next();
+        if (d == 0) continue;
+        uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+        uint32_t gb = gb0 + mag - 1;
+        if (SCATTER) {
+            uint32_t pos = atomicAdd(&counters[gb], 1u);
+            entries[pos] = pid | (d < 0 ? 0x80000000u : 0u);
+        } else {
+            atomicAdd(&counters[gb], 1u);
+        }
+    }
+}
+
+// ---- stage 2: exclusive scan of u32 (three-kernel, 4096 items per block) ------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                            uint32_t n, uint32_t* __restrict__ tile_sums) {
+    __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < n) ? in[base + i] : 0u;
+        sum += v[i];
+    }
+    // inclusive warp scan of the per-thread sums
+    uint32_t inc = sum;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < SCAN_THREADS / 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, ws, o);
+            if (lane >= o) ws += y;
+        }
+        if (lane < SCAN_THREADS / 32) warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    uint32_t excl = inc - sum + (wid ? warp_sums[wid - 1] : 0u);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = excl;
+        excl += v[i];
+    }
+    if (threadIdx.x == SCAN_THREADS - 1 && tile_sums) tile_sums[blockIdx.x] = excl;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t* __restrict__ data, uint32_t n,
+                                                           const uint32_t* __restrict__ tile_offsets) {
+    const uint32_t add = tile_offsets[blockIdx.x];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+        if (base + i < n) data[base + i] += add;
+}
+
+// out may alias in
+void exclusive_scan_u32(Arena& ar, const uint32_t* in, uint32_t* out, uint32_t n) {
+    const unsigned tiles = div_up(n, SCAN_TILE);
+    if (tiles == 1) {
+        SONIC_LAUNCH(k_scan_tile, 1, SCAN_THREADS, 0, in, out, n, (uint32_t*)nullptr);
+        return;
+    }
+    uint32_t* sums = ar.get<uint32_t>(tiles);
+    SONIC_LAUNCH(k_scan_tile, tiles, SCAN_THREADS, 0, in, out, n, sums);
+    exclusive_scan_u32(ar, sums, sums, tiles);
+    SONIC_LAUNCH(k_scan_add, tiles, SCAN_THREADS, 0, out, n, sums);
+}
+
+// ---- stage 4: chunked bucket accumulation (the hot kernel) -------------------------------
+SONIC_D G1Affine fetch_entry(const G1Affine* __restrict__ points, uint32_t e) {
+    G1Affine p = load_affine(points + (e & 0x7fffffffu));
+    if (e & 0x80000000u) p.y = fp_neg(p.y);  // entries never reference the point at infinity's y: neg(0)=0
+    return p;
+}
+
+__global__ void __launch_bounds__(128, 3)
+k_msm_accumulate(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets, uint32_t GB,
+                 uint32_t L, const G1Affine* __restrict__ points,
+                 G1XYZZ* __restrict__ buckets, G1XYZZ* __restrict__ head, G1XYZZ* __restrict__ tail) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total = offsets[GB];  // number of non-zero digits; the grid is sized for the upper bound
+    const uint64_t start64 = (uint64_t)t * L;
+    if (start64 >= total) return;
+    const uint32_t start = (uint32_t)start64;
+    const uint32_t end = (total - start < L) ? total : start + L;
+    // bucket that holds entry `start`: last gb with offsets[gb] <= start (non-empty by construction)
+    uint32_t lo = 0, hi = GB;  // invariant: offsets[lo] <= start < offsets[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= start) lo = mid; else hi = mid;
+    }
+    uint32_t gb = lo;
+    uint32_t bend = offsets[gb + 1];
+    while (bend <= start) { ++gb; bend = offsets[gb + 1]; }  // (defensive; lo already satisfies it)
+    bool cont = offsets[gb] < start;  // bucket began in an earlier chunk
+    bool fresh = true;
+    G1XYZZ acc = G1XYZZ::inf();
+    for (uint32_t p = start; p < end; ++p) {
+        G1Affine pt = fetch_entry(points, entries[p]);
+        if (fresh) { acc = G1XYZZ::from_affine(pt); fresh = false; }
+        else g1_madd(acc, pt);
+        if (p + 1 == bend || p + 1 == end) {
+            if (cont) store_xyzz(head + t, acc);
+            else if (bend <= end) store_xyzz(buckets + gb, acc);
+            else store_xyzz(tail + t, acc);
+            if (p + 1 < end) {
+                do { ++gb; bend = offsets[gb + 1]; } while (bend <= p + 1);
+                cont = false;
+                fresh = true;
+            }
+        }
+    }
+}
+
+// ---- block-wide sum of XYZZ points through shared memory --------------------------------
+template <int THREADS>
+SONIC_D G1XYZZ block_sum_xyzz(G1XYZZ v, G1XYZZ* smem) {
+    smem[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            g1_add(v, smem[threadIdx.x + s]);
+            smem[threadIdx.x] = v;
+        }
+        __syncthreads();
+    }
+    return v;  // valid in thread 0
+}
+
+// ---- stage 5: fold the pieces of buckets that straddle chunk borders ---------------------
+__global__ void __launch_bounds__(128)
+k_msm_fixup(const uint32_t* __restrict__ offsets, uint32_t GB, uint32_t L, G1XYZZ* __restrict__ buckets,
+            const G1XYZZ* __restrict__ head, const G1XYZZ* __restrict__ tail,
+            uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ heavy_list) {
+    const uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gb >= GB) return;
+    const uint32_t a = offsets[gb], b = offsets[gb + 1];
+    if (a == b) { store_xyzz(buckets + gb, G1XYZZ::inf()); return; }
+    const uint32_t t0 = a / L, t1 = (b - 1) / L;
+    if (t0 == t1) return;  // written whole by the accumulate kernel
+    if (t1 - t0 + 1 > (uint32_t)MSM_HEAVY_PIECES) {
+        heavy_list[atomicAdd(heavy_count, 1u)] = gb;
+        return;
+    }
+    G1XYZZ acc = load_xyzz(tail + t0);
+    for (uint32_t t = t0 + 1; t <= t1; ++t) g1_add(acc, load_xyzz(head + t));
+    store_xyzz(buckets + gb, acc);
+}
+
+__global__ void __launch_bounds__(MSM_RED_THREADS)
+k_msm_heavy(const uint32_t* __restrict__ offsets, uint32_t L, G1XYZZ* __restrict__ buckets,
+            const G1XYZZ* __restrict__ head, const G1XYZZ* __restrict__ tail,
+            const uint32_t* __restrict__ heavy_count, const uint32_t* __restrict__ heavy_list) {
+    __shared__ G1XYZZ smem[MSM_RED_THREADS];
+    const uint32_t nh = *heavy_count;
+    for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
+        const uint32_t gb = heavy_list[h];
+        const uint32_t a = offsets[gb], b = offsets[gb + 1];
+        const uint32_t t0 = a / L, t1 = (b - 1) / L;
+        G1XYZZ acc = G1XYZZ::inf();
+        for (uint32_t t = t0 + threadIdx.x; t <= t1; t += MSM_RED_THREADS)
+            g1_add(acc, load_xyzz(t == t0 ? tail + t0 : head + t));
+        acc = block_sum_xyzz<MSM_RED_THREADS>(acc, smem);
+        if (threadIdx.x == 0) store_xyzz(buckets + gb, acc);
+        __syncthreads();
+    }
+}
+
+// ---- stage 6: per-window bucket reduction  sum_b (b+1) * B_b ------------------------------
+// grid = (blocks_per_window, windows_total); each thread owns K consecutive buckets.
+__global__ void __launch_bounds__(MSM_RED_THREADS)
+k_msm_bucket_reduce(const G1XYZZ* __restrict__ buckets, uint32_t B, uint32_t K, G1XYZZ* __restrict__ partial) {
+    __shared__ G1XYZZ smem[MSM_RED_THREADS];
+    const uint32_t window = blockIdx.y;
+    const uint32_t first = (blockIdx.x * MSM_RED_THREADS + threadIdx.x) * K;  // 0-based bucket index in window
+    G1XYZZ run = G1XYZZ::inf(), acc = G1XYZZ::inf();
+    if (first < B) {
+        const G1XYZZ* bp = buckets + (size_t)window * B + first;
+        const uint32_t kmax = (B - first < K) ? (B - first) : K;
+        for (uint32_t k = kmax; k-- > 0;) {
+            g1_add(run, load_xyzz(bp + k));
+            g1_add(acc, run);
+        }
+        // weights are (bucket index + 1): add first * (sum of the K buckets)
+        if (first) {
+            G1XYZZ m = G1XYZZ::inf();
+            for (int bit = 31 - __clz(first); bit >= 0; --bit) {
+                m = g1_dbl(m);
+                if ((first >> bit) & 1) g1_add(m, run);
+            }
+            g1_add(acc, m);
+        }
+    }
+    acc = block_sum_xyzz<MSM_RED_THREADS>(acc, smem);
+    if (threadIdx.x == 0) store_xyzz(partial + (size_t)window * gridDim.x + blockIdx.x, acc);
+}
+
+// ---- stage 7: per job: fold window partials, Horner over windows, affine, compress ---------
+__global__ void __launch_bounds__(64)
+k_msm_finish(const G1XYZZ* __restrict__ partial, uint32_t S, int W, int c, G1Affine* __restrict__ out_aff,
+             uint8_t* __restrict__ out_comp) {
+    __shared__ G1XYZZ win[64];
+    const uint32_t job = blockIdx.x;
+    if ((int)threadIdx.x < W) {
+        const G1XYZZ* pp = partial + ((size_t)job * W + threadIdx.x) * S;
+        G1XYZZ acc = load_xyzz(pp);
+        for (uint32_t s = 1; s < S; ++s) g1_add(acc, load_xyzz(pp + s));
+        win[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        G1XYZZ acc = win[W - 1];
+        for (int w = W - 2; w >= 0; --w) {
+            for (int i = 0; i < c; ++i) acc = g1_dbl(acc);
+            g1_add(acc, win[w]);
+        }
+        G1Affine a = g1_to_affine(acc);
+        if (out_aff) out_aff[job] = a;
+        if (out_comp) g1_compress(a, out_comp + (size_t)job * 48);
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------
+struct MsmPlan {
+    int c, W;
+    uint32_t B, GB, L, K, S, n_tot;
+};
+
+static MsmPlan msm_plan(const Ctx& cx, uint32_t n_tot, int M) {
+    MsmPlan p;
+    int best_c = 8;
+    double best = 1e300;
+    for (int c = 4; c <= 20; ++c) {
+        int W = msm_num_windows(c);
+        if (W > 64) continue;
+        double B = double(1u << (c - 1));
+        double buckets = double(M) * W * B;
+        if (buckets > 3.0e8) continue;
+        // mixed add = 1.0, full add = 1.4; reduction ~ 2 adds + fix-up traffic per bucket
+        double cost = double(n_tot) * W + buckets * (2 * 1.4 + 0.6);
+        if (cost < best) { best = cost; best_c = c; }
+    }
+    p.c = cx.opt_window_bits > 0 ? cx.opt_window_bits : best_c;
+    if (p.c < 4) p.c = 4;
+    if (p.c > 20) p.c = 20;
+    p.W = msm_num_windows(p.c);
+    p.B = 1u << (p.c - 1);
+    p.GB = (uint32_t)M * p.W * p.B;
+    p.n_tot = n_tot;
+    // chunk length: enough chunks to fill the machine a few times over, capped for low fix-up cost
+    uint64_t entries = (uint64_t)n_tot * p.W;
+    uint64_t want_threads = (uint64_t)cx.sm_count * 384 * 6;
+    uint64_t L = entries / (want_threads ? want_threads : 1);
+    if (L < 8) L = 8;
+    if (L > 64) L = 64;
+    p.L = cx.opt_chunk > 0 ? (uint32_t)cx.opt_chunk : (uint32_t)L;
+    p.K = p.B / MSM_RED_THREADS;
+    if (p.K < 1) p.K = 1;
+    if (p.K > 8) p.K = 8;
+    p.S = div_up(p.B, (uint64_t)MSM_RED_THREADS * p.K);
+    return p;
+}
+
+// d_scalars: canonical little-endian scalars, 8 words each.  Results: one affine point
+// (Montgomery form) and/or one 48-byte compressed encoding per job, in device memory.
+void msm_run(Ctx& cx, const G1Affine* d_points, const uint32_t* d_scalars,
+                    const std::vector<MsmJob>& jobs, G1Affine* d_out_aff, uint8_t* d_out_comp) {
+    const int M = (int)jobs.size();
+    if (M == 0) return;
+    if (M > MSM_MAX_JOBS) throw CudaError{cudaErrorInvalidValue, "too many MSM jobs", __LINE__};
+    MsmJobTable tab;
+    memset(&tab, 0, sizeof tab);
+    tab.M = M;
+    uint64_t n_tot64 = 0;
+    for (int i = 0; i < M; ++i) {
+        tab.job[i] = jobs[i];
+        tab.prefix[i] = (uint32_t)n_tot64;
+        n_tot64 += jobs[i].n;
+    }
+    tab.prefix[M] = (uint32_t)n_tot64;
+    if (n_tot64 >= (1ull << 31)) throw CudaError{cudaErrorInvalidValue, "MSM batch too large", __LINE__};
+    const uint32_t n_tot = (uint32_t)n_tot64;
+    Arena& ar = cx.arena;
+    MsmPlan p = msm_plan(cx, n_tot, M);
+    if ((uint64_t)n_tot * p.W >= (1ull << 32)) throw CudaError{cudaErrorInvalidValue, "MSM batch too large", __LINE__};
+    cudaStream_t st = cx.stream;
+
+    SONIC_CUDA(cudaEventRecord(cx.ev[0], st));
+    uint32_t* offsets = ar.get<uint32_t>((size_t)p.GB + 1);
+    uint32_t* cursors = ar.get<uint32_t>((size_t)p.GB + 1);
+    SONIC_CUDA(cudaMemsetAsync(offsets, 0, ((size_t)p.GB + 1) * 4, st));
+    if (n_tot) SONIC_LAUNCH(k_msm_digits<false>, div_up(n_tot, 256), 256, 0, d_scalars, tab, n_tot, p.c, p.W, p.B, offsets, (uint32_t*)nullptr);
+    exclusive_scan_u32(ar, offsets, offsets, p.GB + 1);
+    SONIC_CUDA(cudaMemcpyAsync(cursors, offsets, ((size_t)p.GB + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    // zero digits are not stored, so n_tot*W is only an upper bound of the entry count; the
+    // accumulate grid is sized for the bound and reads the true count from offsets[GB]
+    const uint64_t total_max = (uint64_t)n_tot * p.W;
+    uint32_t* entries = ar.get<uint32_t>(total_max ? total_max : 1);
+    if (n_tot) SONIC_LAUNCH(k_msm_digits<true>, div_up(n_tot, 256), 256, 0, d_scalars, tab, n_tot, p.c, p.W, p.B, cursors, entries);
+    SONIC_CUDA(cudaEventRecord(cx.ev[1], st));
+
+    const uint32_t chunks = div_up(total_max, p.L);
+    G1XYZZ* buckets = ar.get<G1XYZZ>(p.GB);
+    G1XYZZ* head = ar.get<G1XYZZ>(chunks ? chunks : 1);
+    G1XYZZ* tail = ar.get<G1XYZZ>(chunks ? chunks : 1);
+    if (chunks) SONIC_LAUNCH(k_msm_accumulate, div_up(chunks, 128), 128, 0, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
+    uint32_t* heavy_count = ar.get<uint32_t>(1);
+    uint32_t* heavy_list = ar.get<uint32_t>((size_t)chunks / MSM_HEAVY_PIECES + 2);
+    SONIC_CUDA(cudaMemsetAsync(heavy_count, 0, 4, st));
+    SONIC_LAUNCH(k_msm_fixup, div_up(p.GB, 128), 128, 0, offsets, p.GB, p.L, buckets, head, tail, heavy_count, heavy_list);
+    SONIC_LAUNCH(k_msm_heavy, cx.sm_count * 2, MSM_RED_THREADS, 0, offsets, p.L, buckets, head, tail, heavy_count, heavy_list);
+    SONIC_CUDA(cudaEventRecord(cx.ev[2], st));
+
+    G1XYZZ* partial = ar.get<G1XYZZ>((size_t)M * p.W * p.S);
+    SONIC_LAUNCH(k_msm_bucket_reduce, dim3(p.S, (unsigned)(M * p.W)), MSM_RED_THREADS, 0, buckets, p.B, p.K, partial);
+    SONIC_LAUNCH(k_msm_finish, M, 64, 0, partial, p.S, p.W, p.c, d_out_aff, d_out_comp);
+    SONIC_CUDA(cudaEventRecord(cx.ev[3], st));
+}
+
+void msm_collect_timing(Ctx& cx) {
+    float a = 0, b = 0, c = 0;
+    if (cudaEventElapsedTime(&a, cx.ev[0], cx.ev[1]) == cudaSuccess &&
+        cudaEventElapsedTime(&b, cx.ev[1], cx.ev[2]) == cudaSuccess &&
+        cudaEventElapsedTime(&c, cx.ev[2], cx.ev[3]) == cudaSuccess) {
+        cx.timing_ms["msm.sort"] = a;
+        cx.timing_ms["msm.accumulate"] = b;
+        cx.timing_ms["msm.reduce"] = c;
+        cx.timing_ms["msm"] = a + b + c;
+    }
+}
+
+
+}  // namespace sonic

@@ -1,0 +1,300 @@
+// Fr-side kernels: the Laurent-polynomial arithmetic that feeds the commitments.
+//
+// Dense vectors stand in for the reference's sparse `VLaurent Fr`: a vector plus the
+// exponent `lo` of its first slot.  Zero slots are exactly the terms the sparse form does
+// not hold.  All values on the device are in Montgomery form unless a name says "canon".
+//
+//   power tables      base^k                      (Utils.hs:18 `pow`, CommitmentScheme.hs:43 `eval`)
+//   open              f(z) and (f(X)-f(z))/(X-z)  (CommitmentScheme.hs:43-44)
+//   NTT               radix-2 over Fr, 2-adicity 32, for t(X,y) (Constraints.hs:61)
+#include "internal.h"
+
+namespace sonic {
+
+// ---- conversions ------------------------------------------------------------------------
+__global__ void k_fr_to_mont(const Fr* __restrict__ in, Fr* __restrict__ out, uint64_t n, uint32_t* __restrict__ bad) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr v = in[i];
+    // canonical check: v < r
+    uint32_t t = Chain::sub_cc(v.l[0], FrParams::P(0));
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t = Chain::subc_cc(v.l[k], FrParams::P(k));
+    if (Chain::subc(0, 0) == 0 && bad) atomicExch(bad, 1u);  // no borrow: v >= r
+    (void)t;
+    out[i] = fp_to_mont(v);
+}
+
+__global__ void k_fr_from_mont(const Fr* __restrict__ in, Fr* __restrict__ out, uint64_t n) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = fp_from_mont(in[i]);
+}
+
+// out[i] = 1/in[i]  (0 -> 0), a few elements only
+__global__ void k_fr_inv(const Fr* __restrict__ in, Fr* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = fp_inv(in[i]);
+}
+
+// ---- power tables: tab[t][k] = base[t]^k, k in [0, len) -------------------------------------
+constexpr int POW_RUN = 16;
+__global__ void __launch_bounds__(128) k_pow_tables(const Fr* __restrict__ bases, Fr* __restrict__ tab, uint64_t len, uint64_t stride) {
+    const uint64_t k0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * POW_RUN;
+    if (k0 >= len) return;
+    const Fr b = bases[blockIdx.y];
+    Fr v = fp_pow_u64(b, k0);
+    Fr* o = tab + (size_t)blockIdx.y * stride + k0;
+    for (int i = 0; i < POW_RUN && k0 + i < len; ++i) {
+        o[i] = v;
+        v = fp_mul(v, b);
+    }
+}
+
+// ---- warp / block reductions over Fr -------------------------------------------------------
+SONIC_D Fr fr_shfl_down(const Fr& v, int o) {
+    Fr r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.l[k] = __shfl_down_sync(0xffffffffu, v.l[k], o);
+    return r;
+}
+
+// sum over the block; result valid in thread 0.  smem: one Fr per warp.
+template <int THREADS>
+SONIC_D Fr block_sum_fr(Fr v, Fr* smem) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Fr y = fr_shfl_down(v, o);
+        v = fp_add(v, y);  // lanes beyond the edge add garbage that is never read by lane 0
+    }
+    if (lane == 0) smem[wid] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < THREADS / 32; ++w) v = fp_add(v, smem[w]);
+    }
+    return v;
+}
+
+// ---- openPoly -----------------------------------------------------------------------------
+// One "open job": f over exponents [lo, lo+len) (lo <= 0 < lo+len), evaluation point z given
+// through its tables pz[k] = z^k, pzi[k] = z^-k.  With h_k = f_k z^k and H = sum_k h_k:
+//   f(z) = z^lo * H,
+//   quotient q_(k-1) = z^-k * sum_(m>=k) h'_m,   h' = h with H subtracted at slot -lo
+// which is the synthetic division (f(X) - f(z)) / (X - z) written as a suffix sum.
+
+constexpr int OPEN_THREADS = 256;
+constexpr int OPEN_ITEMS = 4;
+constexpr int OPEN_TILE = OPEN_THREADS * OPEN_ITEMS;
+
+// pass 1: per-tile sums of h
+__global__ void __launch_bounds__(OPEN_THREADS) k_open_partial(const OpenJob* __restrict__ jobs, Fr* __restrict__ partial, uint32_t tiles_stride) {
+    __shared__ Fr smem[OPEN_THREADS / 32];
+    const OpenJob jb = jobs[blockIdx.y];
+    const uint32_t base = blockIdx.x * OPEN_TILE + threadIdx.x * OPEN_ITEMS;
+    if (blockIdx.x * OPEN_TILE >= jb.len) return;
+    Fr s = Fr::zero();
+#pragma unroll
+    for (int i = 0; i < OPEN_ITEMS; ++i) {
+        const uint32_t k = base + i;
+        if (k < jb.len) s = fp_add(s, fp_mul(jb.f[k], jb.pz[k]));
+    }
+    s = block_sum_fr<OPEN_THREADS>(s, smem);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.y * tiles_stride + blockIdx.x] = s;
+}
+
+// pass 2 (one block per job): H, f(z), and the exclusive suffix sums of the tile sums
+__global__ void __launch_bounds__(256) k_open_tiles(const OpenJob* __restrict__ jobs, Fr* __restrict__ partial, uint32_t tiles_stride, Fr* __restrict__ Hout) {
+    const OpenJob jb = jobs[blockIdx.x];
+    if (threadIdx.x != 0) return;
+    Fr* p = partial + (size_t)blockIdx.x * tiles_stride;
+    const uint32_t tiles = (jb.len + OPEN_TILE - 1) / OPEN_TILE;
+    Fr H = Fr::zero();
+    for (uint32_t t = 0; t < tiles; ++t) H = fp_add(H, p[t]);
+    Hout[blockIdx.x] = H;
+    Fr fz;
+    if (jb.z_is_zero) fz = jb.f[-jb.lo];           // only reached with lo == 0 (host rejects lo < 0 at z = 0)
+    else fz = jb.lo < 0 ? fp_mul(H, jb.pzi[-jb.lo]) : fp_mul(H, jb.pz[jb.lo]);
+    *jb.value_canon = fp_from_mont(fz);
+    // exclusive suffix over tiles of h' (H removed from the tile that holds slot -lo)
+    const uint32_t ct = (uint32_t)(-jb.lo) / OPEN_TILE;
+    Fr run = Fr::zero();
+    for (uint32_t t = tiles; t-- > 0;) {
+        Fr v = p[t];
+        if (t == ct) v = fp_sub(v, H);
+        p[t] = run;
+        run = fp_add(run, v);
+    }
+}
+
+// pass 3: in-tile suffix scan, scale by z^-k, emit canonical quotient coefficients
+__global__ void __launch_bounds__(OPEN_THREADS) k_open_quotient(const OpenJob* __restrict__ jobs, const Fr* __restrict__ partial, uint32_t tiles_stride, const Fr* __restrict__ Hin) {
+    __shared__ Fr wsum[OPEN_THREADS / 32];
+    const OpenJob jb = jobs[blockIdx.y];
+    if (jb.q_canon == nullptr || blockIdx.x * OPEN_TILE >= jb.len) return;
+    const uint32_t base = blockIdx.x * OPEN_TILE + threadIdx.x * OPEN_ITEMS;
+    if (jb.z_is_zero) {
+        // X - 0 divides f - f(0): the quotient is a shift
+#pragma unroll
+        for (int i = 0; i < OPEN_ITEMS; ++i) {
+            const uint32_t k = base + i;
+            if (k >= 1 && k < jb.len) jb.q_canon[k - 1] = fp_from_mont(jb.f[k]);
+        }
+        return;
+    }
+    const Fr H = Hin[blockIdx.y];
+    const uint32_t c = (uint32_t)(-jb.lo);
+    Fr h[OPEN_ITEMS];
+#pragma unroll
+    for (int i = 0; i < OPEN_ITEMS; ++i) {
+        const uint32_t k = base + i;
+        h[i] = Fr::zero();
+        if (k < jb.len) {
+            h[i] = fp_mul(jb.f[k], jb.pz[k]);
+            if (k == c) h[i] = fp_sub(h[i], H);
+        }
+    }
+    // thread-local inclusive suffix
+#pragma unroll
+    for (int i = OPEN_ITEMS - 2; i >= 0; --i) h[i] = fp_add(h[i], h[i + 1]);
+    // exclusive suffix across the block of the thread totals h[0]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    Fr inc = h[0];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        Fr y = fr_shfl_down(inc, o);
+        if (lane + o < 32) inc = fp_add(inc, y);
+    }
+    if (lane == 0) wsum[wid] = inc;
+    __syncthreads();
+    Fr off = partial[(size_t)blockIdx.y * tiles_stride + blockIdx.x];
+    for (int w = OPEN_THREADS / 32 - 1; w > wid; --w) off = fp_add(off, wsum[w]);
+    off = fp_add(off, fp_sub(inc, h[0]));  // lanes above in this warp
+#pragma unroll
+    for (int i = 0; i < OPEN_ITEMS; ++i) {
+        const uint32_t k = base + i;
+        if (k >= 1 && k < jb.len) {
+            Fr S = fp_add(h[i], off);
+            jb.q_canon[k - 1] = fp_from_mont(fp_mul(S, jb.pzi[k]));
+        }
+    }
+}
+
+// ---- NTT ------------------------------------------------------------------------------------
+// Radix-2, in place.  Forward = decimation in frequency (natural in, bit-reversed out);
+// inverse = decimation in time on the bit-reversed data (natural out), so a cyclic
+// convolution needs no permutation.  tw[k] = omega^k, k < L/2 (omega^-k for the inverse).
+__global__ void __launch_bounds__(256) k_ntt_dif_stage(Fr* __restrict__ a, const Fr* __restrict__ tw, uint32_t logL, uint32_t stage) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // butterfly index < L/2
+    if (i >= (1u << (logL - 1))) return;
+    const uint32_t half = 1u << (logL - 1 - stage);
+    const uint32_t j = i & (half - 1);
+    const uint32_t lo = ((i - j) << 1) + j;
+    const Fr u = a[lo], v = a[lo + half];
+    a[lo] = fp_add(u, v);
+    a[lo + half] = fp_mul(fp_sub(u, v), tw[j << stage]);
+}
+
+__global__ void __launch_bounds__(256) k_ntt_dit_stage(Fr* __restrict__ a, const Fr* __restrict__ tw, uint32_t logL, uint32_t stage) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1u << (logL - 1))) return;
+    const uint32_t half = 1u << stage;  // stage 0 first: smallest butterflies
+    const uint32_t j = i & (half - 1);
+    const uint32_t lo = ((i - j) << 1) + j;
+    const Fr u = a[lo];
+    const Fr v = fp_mul(a[lo + half], tw[j << (logL - 1 - stage)]);
+    a[lo] = fp_add(u, v);
+    a[lo + half] = fp_sub(u, v);
+}
+
+__global__ void __launch_bounds__(256) k_fr_mul_pointwise(Fr* __restrict__ a, const Fr* __restrict__ b, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = fp_mul(a[i], b[i]);
+}
+
+__global__ void __launch_bounds__(256) k_fr_scale(Fr* __restrict__ a, const Fr* __restrict__ s, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = fp_mul(a[i], *s);
+}
+
+// omega_L = ROOT32^(2^(32-logL)); params[0] = omega, [1] = omega^-1, [2] = 1/L
+__global__ void k_ntt_params(uint32_t logL, Fr* __restrict__ params) {
+    if (threadIdx.x != 0) return;
+    Fr w, wi;
+    for (int k = 0; k < 8; ++k) { w.l[k] = FrParams::ROOT32_M(k); wi.l[k] = FrParams::ROOT32_INV_M(k); }
+    for (uint32_t s = logL; s < 32; ++s) { w = fp_sqr(w); wi = fp_sqr(wi); }
+    params[0] = w;
+    params[1] = wi;
+    Fr L = Fr::zero();
+    L.l[0] = 1u << logL;  // logL <= 31
+    params[2] = fp_inv(fp_to_mont(L));
+}
+
+
+NttPlan ntt_prepare(Ctx& cx, uint32_t logL) {
+    NttPlan p;
+    p.logL = logL;
+    const uint64_t half = logL ? (1ull << (logL - 1)) : 1;
+    p.params = cx.arena.get<Fr>(3);
+    Fr* tabs = cx.arena.get<Fr>(2 * half);
+    p.tw = tabs;
+    p.twi = tabs + half;
+    SONIC_LAUNCH(k_ntt_params, 1, 32, 0, logL, p.params);
+    SONIC_LAUNCH(k_pow_tables, dim3(div_up(div_up(half, POW_RUN), 128), 2), 128, 0, p.params, tabs, half, half);
+    return p;
+}
+
+void ntt_forward(const NttPlan& p, Fr* a) {
+    const uint32_t half = 1u << (p.logL - 1);
+    for (uint32_t s = 0; s < p.logL; ++s) SONIC_LAUNCH(k_ntt_dif_stage, div_up(half, 256), 256, 0, a, p.tw, p.logL, s);
+}
+
+void ntt_inverse(const NttPlan& p, Fr* a) {
+    const uint32_t half = 1u << (p.logL - 1);
+    for (uint32_t s = 0; s < p.logL; ++s) SONIC_LAUNCH(k_ntt_dit_stage, div_up(half, 256), 256, 0, a, p.twi, p.logL, s);
+    SONIC_LAUNCH(k_fr_scale, div_up(2 * half, 256), 256, 0, a, p.params + 2, 2 * half);
+}
+
+
+// ---- host launchers ---------------------------------------------------------------------------
+void fr_to_mont(Ctx& cx, const Fr* in, Fr* out, uint64_t n, uint32_t* bad_flag) {
+    (void)cx;
+    if (n) SONIC_LAUNCH(k_fr_to_mont, div_up(n, 256), 256, 0, in, out, n, bad_flag);
+}
+
+void fr_from_mont(Ctx& cx, const Fr* in, Fr* out, uint64_t n) {
+    (void)cx;
+    if (n) SONIC_LAUNCH(k_fr_from_mont, div_up(n, 256), 256, 0, in, out, n);
+}
+
+void fr_inv_few(Ctx& cx, const Fr* in, Fr* out, int n) {
+    (void)cx;
+    if (n) SONIC_LAUNCH(k_fr_inv, div_up(n, 32), 32, 0, in, out, n);
+}
+
+void fr_mul_pointwise(Ctx& cx, Fr* a, const Fr* b, uint32_t n) {
+    (void)cx;
+    if (n) SONIC_LAUNCH(k_fr_mul_pointwise, div_up(n, 256), 256, 0, a, b, n);
+}
+
+void pow_tables(Ctx& cx, const Fr* bases, int ntab, Fr* tab, uint64_t len, uint64_t stride) {
+    (void)cx;
+    if (ntab && len) SONIC_LAUNCH(k_pow_tables, dim3(div_up(div_up(len, POW_RUN), 128), (unsigned)ntab), 128, 0, bases, tab, len, stride);
+}
+
+void open_batch(Ctx& cx, const std::vector<OpenJob>& jobs) {
+    const int nj = (int)jobs.size();
+    if (!nj) return;
+    uint32_t max_len = 0;
+    for (const OpenJob& j : jobs) max_len = j.len > max_len ? j.len : max_len;
+    const uint32_t tiles = div_up(max_len ? max_len : 1, OPEN_TILE);
+    OpenJob* d_jobs = cx.arena.get<OpenJob>(nj);
+    SONIC_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(OpenJob) * nj, cudaMemcpyHostToDevice, cx.stream));
+    Fr* partial = cx.arena.get<Fr>((size_t)tiles * nj);
+    Fr* H = cx.arena.get<Fr>(nj);
+    SONIC_LAUNCH(k_open_partial, dim3(tiles, (unsigned)nj), OPEN_THREADS, 0, d_jobs, partial, tiles);
+    SONIC_LAUNCH(k_open_tiles, nj, 32, 0, d_jobs, partial, tiles, H);
+    SONIC_LAUNCH(k_open_quotient, dim3(tiles, (unsigned)nj), OPEN_THREADS, 0, d_jobs, partial, tiles, H);
+    // the job table is read by kernels still in flight: the caller keeps `jobs` alive until it synchronises
+}
+
+}  // namespace sonic

@@ -1,0 +1,495 @@
+// Device-side orchestration of the Sonic prover (one call per proof).
+//
+// Reference: `prove` (src/Sonic/Protocol.hs:47-109) and `hscProve`
+// (src/Sonic/Signature.hs:32-72).  The reference builds bivariate sparse polynomials and
+// evaluates one variable at a time; every polynomial it ever commits to or opens is
+// univariate, so the device builds those univariate vectors directly:
+//
+//   r'(X,1)   Constraints.hs:23-31 + Protocol.hs:58-62      dense over X^{-2n-4..n}
+//   s(X,y)    Constraints.hs:34-53 then Utils.hs:20-21      dense over X^{-n..2n}
+//   s(u,Y)    Constraints.hs:34-53 then Utils.hs:17-18      dense over Y^{-n..n+Q}
+//   t(X,y)    Constraints.hs:56-65 then Utils.hs:20-21      = r'(X,1) * (r'(X,y) + s(X,y)) - k(y),
+//             one cyclic convolution of length 2^ceil(log2(7n+9)) by NTT, dense over X^{-4n-8..3n}
+//
+// All 2Q+8 random field elements arrive up front in the reference's draw order (they are
+// sampled, not derived from the transcript), so the whole proof is one call: the Fr work
+// first, then every commitment and opening of the proof as ONE batched MSM launch.
+#include <algorithm>
+
+#include "internal.h"
+
+namespace sonic {
+
+// ---- vector builders -----------------------------------------------------------------------
+// r'(X,1): slot k <-> exponent k - 2n - 4
+__global__ void __launch_bounds__(256) k_build_r(const Fr* __restrict__ aL, const Fr* __restrict__ aR, const Fr* __restrict__ aO,
+                                                 const Fr* __restrict__ cns, uint32_t n, Fr* __restrict__ out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 3 * n + 5) return;
+    const int64_t e = (int64_t)k - 2 * (int64_t)n - 4;
+    Fr v = Fr::zero();
+    if (e >= 1) v = aL[e - 1];                                   // a_i X^i
+    else if (e <= -1 && e >= -(int64_t)n) v = aR[-e - 1];        // b_i X^-i
+    else if (e < -(int64_t)n && e >= -2 * (int64_t)n) v = aO[-e - n - 1];  // c_i X^(-i-n)
+    else if (e < -2 * (int64_t)n) v = cns[-e - 2 * (int64_t)n - 1];        // c_(n+i) X^(-2n-i)
+    out[k] = v;
+}
+
+// s(X,y) for several y at once: grid.y selects the evaluation point.
+// out[b][k], slot k <-> exponent k - n, k in [0, 3n]
+__global__ void __launch_bounds__(128) k_build_sxy(const Fr* __restrict__ wL, const Fr* __restrict__ wR, const Fr* __restrict__ wO,
+                                                   uint32_t n, uint32_t Q, const Fr* __restrict__ tabs, uint64_t tl,
+                                                   const uint32_t* __restrict__ fwd_idx, const uint32_t* __restrict__ inv_idx,
+                                                   Fr* __restrict__ out) {
+    const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 >= n) return;
+    const uint32_t b = blockIdx.y;
+    const Fr* yt = tabs + (size_t)fwd_idx[b] * tl;   // y^k
+    const Fr* yi = tabs + (size_t)inv_idx[b] * tl;   // y^-k
+    const uint32_t i = i0 + 1;
+    Fr su = Fr::zero(), sv = Fr::zero(), sw = Fr::zero();
+    for (uint32_t q = 1; q <= Q; ++q) {
+        const Fr yp = yt[n + q];
+        const size_t w = (size_t)(q - 1) * n + i0;
+        su = fp_add(su, fp_mul(yp, wL[w]));
+        sv = fp_add(sv, fp_mul(yp, wR[w]));
+        sw = fp_add(sw, fp_mul(yp, wO[w]));
+    }
+    sw = fp_sub(fp_sub(sw, yt[i]), yi[i]);
+    Fr* o = out + (size_t)b * (3 * (size_t)n + 1);
+    o[n - i] = su;        // u_i(y) X^-i
+    o[n + i] = sv;        // v_i(y) X^i
+    o[2 * n + i] = sw;    // w_i(y) X^(i+n)
+    if (i0 == 0) o[n] = Fr::zero();
+}
+
+// r'(X,y) + s(X,y): slot k <-> exponent k - 2n - 4, k in [0, 4n+4]
+__global__ void __launch_bounds__(256) k_build_rs(const Fr* __restrict__ rX1, const Fr* __restrict__ sXy, const Fr* __restrict__ yt,
+                                                  const Fr* __restrict__ yi, uint32_t n, Fr* __restrict__ out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 4 * n + 5) return;
+    const int64_t e = (int64_t)k - 2 * (int64_t)n - 4;
+    Fr v = Fr::zero();
+    if (e <= (int64_t)n) {
+        const Fr p = e >= 0 ? yt[e] : yi[-e];
+        v = fp_mul(rX1[k], p);  // r'(X,y) = r'(Xy,1)
+    }
+    if (e >= -(int64_t)n) v = fp_add(v, sXy[e + n]);
+    out[k] = v;
+}
+
+// t(X,y) slot 4n+8 (X^0) -= k(y), k(y) = sum_q cs[q] y^(n+1+q)   (Constraints.hs:65,67-68)
+__global__ void k_t_fix(Fr* __restrict__ t, const Fr* __restrict__ cs, const Fr* __restrict__ yt, uint32_t n, uint32_t Q) {
+    if (threadIdx.x || blockIdx.x) return;
+    Fr ky = Fr::zero();
+    for (uint32_t q = 0; q < Q; ++q) ky = fp_add(ky, fp_mul(cs[q], yt[n + 1 + q]));
+    t[4 * n + 8] = fp_sub(t[4 * n + 8], ky);
+}
+
+// s(u,Y): slot k <-> exponent k - n, k in [0, 2n+Q].  +-i slots: -u^(i+n)
+__global__ void __launch_bounds__(256) k_build_suy_pm(const Fr* __restrict__ ut, uint32_t n, uint32_t Q, Fr* __restrict__ out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > 2 * n) return;
+    if (k == n) { out[k] = Fr::zero(); return; }
+    const uint32_t i = k > n ? k - n : n - k;
+    out[k] = fp_neg(ut[i + n]);
+    (void)Q;
+}
+
+// Y^(n+q) slots: sum_i u^-i wL[q][i] + u^i wR[q][i] + u^(i+n) wO[q][i]; one block per q
+__global__ void __launch_bounds__(256) k_build_suy_dot(const Fr* __restrict__ wL, const Fr* __restrict__ wR, const Fr* __restrict__ wO,
+                                                       uint32_t n, const Fr* __restrict__ ut, const Fr* __restrict__ ui,
+                                                       Fr* __restrict__ out) {
+    __shared__ Fr smem[8];
+    const uint32_t q = blockIdx.x;  // 0-based
+    Fr acc = Fr::zero();
+    for (uint32_t i0 = threadIdx.x; i0 < n; i0 += 256) {
+        const uint32_t i = i0 + 1;
+        const size_t w = (size_t)q * n + i0;
+        acc = fp_add(acc, fp_mul(ui[i], wL[w]));
+        acc = fp_add(acc, fp_mul(ut[i], wR[w]));
+        acc = fp_add(acc, fp_mul(ut[i + n], wO[w]));
+    }
+    // block reduction (8 warps)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Fr y;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y.l[k] = __shfl_down_sync(0xffffffffu, acc.l[k], o);
+        acc = fp_add(acc, y);
+    }
+    if (lane == 0) smem[wid] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) acc = fp_add(acc, smem[w]);
+        out[2 * n + 1 + q] = acc;  // exponent n + (q+1)
+    }
+}
+
+// derived scalars: pts[] = the evaluation points (Montgomery), pts[np..2np) their inverses
+// rnd_m: 2M+8 draws (Montgomery), M = number of (y_j, z_j) pairs.  Layout of pts: y, z, yz, y_1..y_M, z_1..z_M, u, v
+__global__ void k_prove_points(const Fr* __restrict__ rnd_m, uint32_t M, int has_main, Fr* __restrict__ pts) {
+    const uint32_t np = 2 * M + 5;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= np) return;
+    Fr v;
+    if (t == 0) v = has_main ? rnd_m[4] : Fr::one();
+    else if (t == 1) v = has_main ? rnd_m[5] : Fr::one();
+    else if (t == 2) v = has_main ? fp_mul(rnd_m[4], rnd_m[5]) : Fr::one();
+    else v = rnd_m[6 + (t - 3)];  // ys, zs, u, v are contiguous in the draw order
+    pts[t] = v;
+    pts[np + t] = fp_inv(v);
+}
+
+// first index in [a, b) (relative to s) whose scalar is non-zero -> atomicMin into *out
+__global__ void __launch_bounds__(256) k_first_nonzero_job(const Fr* __restrict__ s, uint32_t a, uint32_t b, uint32_t* __restrict__ out) {
+    const uint32_t i = a + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b) return;
+    if (!s[i].is_zero()) atomicMin(out, i);
+}
+
+}  // namespace sonic
+
+// resident circuit (weights in Montgomery form)
+struct sonic_circuit {
+    uint64_t n = 0, Q = 0;
+    sonic::Fr* w = nullptr;   // wL | wR | wO, each Q*n row-major, then cs (Q)
+    sonic::Fr* wL() const { return w; }
+    sonic::Fr* wR() const { return w + Q * n; }
+    sonic::Fr* wO() const { return w + 2 * Q * n; }
+    sonic::Fr* cs() const { return w + 3 * Q * n; }
+};
+
+namespace sonic {
+
+int circuit_load(Ctx& cx, uint64_t n, uint64_t Q, const uint8_t* wL, const uint8_t* wR, const uint8_t* wO,
+                 const uint8_t* cs, sonic_circuit** out) {
+    const uint64_t m = Q * n;
+    sonic_circuit* c = new sonic_circuit;
+    c->n = n;
+    c->Q = Q;
+    cudaError_t e = cudaMalloc((void**)&c->w, (3 * m + Q) * sizeof(Fr));
+    if (e != cudaSuccess) { delete c; throw CudaError{e, "cudaMalloc(circuit)", __LINE__}; }
+    try {
+        Fr* stage = cx.arena.get<Fr>(3 * m + Q);
+        SONIC_CUDA(cudaMemcpyAsync(stage, wL, m * 32, cudaMemcpyHostToDevice, cx.stream));
+        SONIC_CUDA(cudaMemcpyAsync(stage + m, wR, m * 32, cudaMemcpyHostToDevice, cx.stream));
+        SONIC_CUDA(cudaMemcpyAsync(stage + 2 * m, wO, m * 32, cudaMemcpyHostToDevice, cx.stream));
+        SONIC_CUDA(cudaMemcpyAsync(stage + 3 * m, cs, Q * 32, cudaMemcpyHostToDevice, cx.stream));
+        uint32_t* bad = cx.arena.get<uint32_t>(1);
+        SONIC_CUDA(cudaMemsetAsync(bad, 0, 4, cx.stream));
+        fr_to_mont(cx, stage, c->w, 3 * m + Q, bad);
+        uint32_t h = 0;
+        SONIC_CUDA(cudaMemcpyAsync(&h, bad, 4, cudaMemcpyDeviceToHost, cx.stream));
+        SONIC_CUDA(cudaStreamSynchronize(cx.stream));
+        if (h) {
+            cudaFree(c->w);
+            delete c;
+            return fail(SONIC_ERR_NONCANONICAL, "a circuit weight is not a canonical residue (>= r)");
+        }
+    } catch (...) {
+        cudaFree(c->w);
+        delete c;
+        throw;
+    }
+    *out = c;
+    return SONIC_OK;
+}
+
+uint64_t circuit_n(const sonic_circuit* c) { return c->n; }
+uint64_t circuit_Q(const sonic_circuit* c) { return c->Q; }
+
+void circuit_free(sonic_circuit* c) {
+    if (!c) return;
+    if (c->w) cudaFree(c->w);
+    delete c;
+}
+
+namespace {
+
+struct Window {  // a dense vector and the exponent of its slot 0
+    Fr* mont = nullptr;
+    Fr* canon = nullptr;
+    int64_t lo = 0;
+    uint32_t len = 0;
+};
+
+// One MSM of the proof, in the order the proof record lists its G1 fields.
+struct ProofMsm {
+    int family;
+    const Fr* scal;   // canonical scalars, slot 0 <-> exponent lo
+    int64_t lo;       // exponent of scalar 0 (already shifted for commits)
+    uint32_t len;
+    bool commit_text;
+};
+
+}  // namespace
+
+// Runs the prover.  d_in: canonical aL | aR | aO (3n Fr, may be null when !has_main) ;
+// d_rnd: canonical draws.  has_main = false computes only the hscProve part, with
+// d_rnd holding ys[Q] zs[Q] u v at the positions they have in the full draw order.
+// Outputs (host): proof bytes in record order.
+int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr* d_in, const Fr* d_rnd,
+              uint32_t M, bool has_main, uint8_t* out, uint64_t cap, uint64_t* written) {
+    const uint32_t n = (uint32_t)circ->n, Q = (uint32_t)circ->Q;
+    const int64_t d = (int64_t)srs->d;
+    const uint32_t nG = has_main ? 4 * M + 7 : 4 * M + 2;
+    const uint32_t nF = has_main ? 2 * M + 5 : 2 * M + 2;
+    const uint64_t need = (uint64_t)nG * 48 + (uint64_t)nF * 32;
+    if (written) *written = need;
+    if (cap < need) return fail(SONIC_ERR_BUFFER_TOO_SMALL, "proof needs %llu bytes", (unsigned long long)need);
+    Arena& ar = cx.arena;
+    cudaStream_t st = cx.stream;
+    SONIC_CUDA(cudaEventRecord(cx.ev[4], st));
+
+    // ---- inputs to Montgomery form (flags non-canonical encodings) ---------------------------
+    const uint32_t nr = 2 * M + 8;
+    uint32_t* bad = ar.get<uint32_t>(1);
+    SONIC_CUDA(cudaMemsetAsync(bad, 0, 4, st));
+    Fr* rnd_m = ar.get<Fr>(nr);
+    fr_to_mont(cx, d_rnd, rnd_m, nr, bad);
+    Fr* in_m = nullptr;
+    if (has_main) {
+        in_m = ar.get<Fr>(3 * (size_t)n);
+        fr_to_mont(cx, d_in, in_m, 3 * (size_t)n, bad);
+    }
+
+    // ---- evaluation points and their power tables ---------------------------------------------
+    const uint32_t np = 2 * M + 5;
+    enum { PT_Y = 0, PT_Z = 1, PT_YZ = 2, PT_YJ = 3 };
+    const uint32_t PT_ZJ = 3 + M, PT_U = 3 + 2 * M, PT_V = 4 + 2 * M;
+    Fr* pts = ar.get<Fr>(2 * np);
+    SONIC_LAUNCH(k_prove_points, div_up(np, 32), 32, 0, rnd_m, M, has_main ? 1 : 0, pts);
+    const uint64_t tl = std::max<uint64_t>(3 * (uint64_t)n + 8, 2 * (uint64_t)n + Q + 4);
+    Fr* tabs = ar.get<Fr>(2 * (size_t)np * tl);
+    pow_tables(cx, pts, 2 * np, tabs, tl, tl);
+    auto fwd = [&](uint32_t p) { return tabs + (size_t)p * tl; };
+    auto inv = [&](uint32_t p) { return tabs + (size_t)(np + p) * tl; };
+    // z also opens t(X,y), 7n+9 long
+    const uint64_t tlz = 7 * (uint64_t)n + 12;
+    Fr* ztabs = nullptr;
+    if (has_main) {
+        ztabs = ar.get<Fr>(2 * tlz);
+        Fr* zb = ar.get<Fr>(2);
+        SONIC_CUDA(cudaMemcpyAsync(zb, pts + PT_Z, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+        SONIC_CUDA(cudaMemcpyAsync(zb + 1, pts + np + PT_Z, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+        pow_tables(cx, zb, 2, ztabs, tlz, tlz);
+    }
+
+    // ---- s(X,y) for y (main) and every y_j ----------------------------------------------------
+    const uint32_t slen = 3 * n + 1;
+    const uint32_t nb = M + 1;  // batch: index 0 = y, 1..M = y_j
+    Fr* sxy_m = ar.get<Fr>((size_t)nb * slen);
+    Fr* sxy_c = ar.get<Fr>((size_t)nb * slen);
+    {
+        std::vector<uint32_t> h_idx(2 * nb);
+        for (uint32_t b = 0; b < nb; ++b) {
+            const uint32_t p = b == 0 ? (uint32_t)PT_Y : (uint32_t)PT_YJ + (b - 1);
+            h_idx[b] = p;
+            h_idx[nb + b] = np + p;
+        }
+        uint32_t* d_idx = ar.get<uint32_t>(2 * nb);
+        SONIC_CUDA(cudaMemcpyAsync(d_idx, h_idx.data(), 8 * nb, cudaMemcpyHostToDevice, st));
+        SONIC_LAUNCH(k_build_sxy, dim3(div_up(n, 128), nb), 128, 0, circ->wL(), circ->wR(), circ->wO(), n, Q, tabs, tl, d_idx, d_idx + nb, sxy_m);
+        fr_from_mont(cx, sxy_m, sxy_c, (size_t)nb * slen);
+    }
+    auto sxy = [&](uint32_t b) { Window w; w.mont = sxy_m + (size_t)b * slen; w.canon = sxy_c + (size_t)b * slen; w.lo = -(int64_t)n; w.len = slen; return w; };
+
+    // ---- s(u,Y) -------------------------------------------------------------------------------
+    Window suy;
+    suy.len = 2 * n + Q + 1;
+    suy.lo = -(int64_t)n;
+    suy.mont = ar.get<Fr>(suy.len);
+    suy.canon = ar.get<Fr>(suy.len);
+    SONIC_LAUNCH(k_build_suy_pm, div_up(2 * n + 1, 256), 256, 0, fwd(PT_U), n, Q, suy.mont);
+    SONIC_LAUNCH(k_build_suy_dot, Q, 256, 0, circ->wL(), circ->wR(), circ->wO(), n, fwd(PT_U), inv(PT_U), suy.mont);
+    fr_from_mont(cx, suy.mont, suy.canon, suy.len);
+
+    // ---- r'(X,1), t(X,y) ------------------------------------------------------------------------
+    Window rx1, txy;
+    if (has_main) {
+        rx1.len = 3 * n + 5;
+        rx1.lo = -2 * (int64_t)n - 4;
+        txy.len = 7 * n + 9;
+        txy.lo = -4 * (int64_t)n - 8;
+        uint32_t logL = 1;
+        while ((1ull << logL) < txy.len) ++logL;
+        const uint64_t L = 1ull << logL;
+        Fr* A = ar.get<Fr>(L);
+        Fr* B = ar.get<Fr>(L);
+        SONIC_CUDA(cudaMemsetAsync(A, 0, L * sizeof(Fr), st));
+        SONIC_CUDA(cudaMemsetAsync(B, 0, L * sizeof(Fr), st));
+        SONIC_LAUNCH(k_build_r, div_up(rx1.len, 256), 256, 0, in_m, in_m + n, in_m + 2 * (size_t)n, rnd_m, n, A);
+        rx1.mont = ar.get<Fr>(rx1.len);
+        rx1.canon = ar.get<Fr>(rx1.len);
+        SONIC_CUDA(cudaMemcpyAsync(rx1.mont, A, rx1.len * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+        fr_from_mont(cx, rx1.mont, rx1.canon, rx1.len);
+        SONIC_LAUNCH(k_build_rs, div_up(4 * n + 5, 256), 256, 0, rx1.mont, sxy_m, fwd(PT_Y), inv(PT_Y), n, B);
+        NttPlan plan = ntt_prepare(cx, logL);
+        ntt_forward(plan, A);
+        ntt_forward(plan, B);
+        fr_mul_pointwise(cx, A, B, (uint32_t)L);
+        ntt_inverse(plan, A);
+        SONIC_LAUNCH(k_t_fix, 1, 32, 0, A, circ->cs(), fwd(PT_Y), n, Q);
+        txy.mont = A;
+        txy.canon = ar.get<Fr>(txy.len);
+        fr_from_mont(cx, txy.mont, txy.canon, txy.len);
+    }
+
+    // ---- openings: values and quotient vectors --------------------------------------------------
+    // values (canonical) collected in one array; quotients in their own buffers
+    std::vector<OpenJob> ojobs;
+    Fr* vals = ar.get<Fr>(3 * (size_t)M + 8);
+    uint32_t nvals = 0;
+    struct Quot { Fr* q; int64_t lo; uint32_t len; };
+    auto add_open = [&](const Window& f, const Fr* pz, const Fr* pzi, bool want_q, uint32_t* val_slot) -> Quot {
+        OpenJob jb;
+        jb.f = f.mont;
+        jb.pz = pz;
+        jb.pzi = pzi;
+        jb.q_canon = want_q ? ar.get<Fr>(f.len) : nullptr;
+        jb.value_canon = vals + nvals;
+        *val_slot = nvals++;
+        jb.len = f.len;
+        jb.lo = (int32_t)f.lo;
+        jb.z_is_zero = 0;
+        jb.pad = 0;
+        ojobs.push_back(jb);
+        return Quot{jb.q_canon, f.lo, f.len - 1};
+    };
+    uint32_t v_a = 0, v_b = 0, v_t = 0, v_s = 0, v_qv = 0;
+    std::vector<uint32_t> v_sj(M), v_spj(M), v_wpj(M);
+    Quot q_a{}, q_b{}, q_t{}, q_v{};
+    std::vector<Quot> q_wj(M), q_wpj(M), q_qj(M);
+    if (has_main) {
+        q_a = add_open(rx1, ztabs, ztabs + tlz, true, &v_a);                 // Protocol.hs:79
+        q_b = add_open(rx1, fwd(PT_YZ), inv(PT_YZ), true, &v_b);            // Protocol.hs:80
+        q_t = add_open(txy, ztabs, ztabs + tlz, true, &v_t);                 // Protocol.hs:81
+        add_open(sxy(0), ztabs, ztabs + tlz, false, &v_s);                   // Protocol.hs:83
+    }
+    for (uint32_t j = 0; j < M; ++j) {
+        q_wj[j] = add_open(sxy(1 + j), fwd(PT_ZJ + j), inv(PT_ZJ + j), true, &v_sj[j]);    // Signature.hs:43
+        q_wpj[j] = add_open(sxy(1 + j), fwd(PT_U), inv(PT_U), true, &v_wpj[j]);            // Signature.hs:54
+        q_qj[j] = add_open(suy, fwd(PT_YJ + j), inv(PT_YJ + j), true, &v_spj[j]);          // Signature.hs:55
+    }
+    q_v = add_open(suy, fwd(PT_V), inv(PT_V), true, &v_qv);                                 // Signature.hs:63
+    open_batch(cx, ojobs);
+    SONIC_CUDA(cudaEventRecord(cx.ev[5], st));
+
+    // ---- the proof's MSMs, in record order -----------------------------------------------------
+    std::vector<ProofMsm> pm;
+    auto commit = [&](const Window& f, int64_t maxm) { pm.push_back(ProofMsm{SONIC_FAMILY_ALPHA, f.canon, f.lo + (d - maxm), f.len, true}); };
+    auto opening = [&](const Quot& q) { pm.push_back(ProofMsm{SONIC_FAMILY_PLAIN, q.q, q.lo, q.len, false}); };
+    if (has_main) {
+        commit(rx1, (int64_t)n);  // prR   Protocol.hs:63
+        commit(txy, d);           // prT   Protocol.hs:73
+        opening(q_a);             // prWa
+        opening(q_b);             // prWb
+        opening(q_t);             // prWt
+    }
+    for (uint32_t j = 0; j < M; ++j) { commit(sxy(1 + j), d); opening(q_wj[j]); }      // hscS   Signature.hs:42-43
+    for (uint32_t j = 0; j < M; ++j) { opening(q_wpj[j]); opening(q_qj[j]); }          // hscW   Signature.hs:54-55
+    opening(q_v);                                                                       // hscQv  Signature.hs:63
+    commit(suy, d);                                                                     // hscC   Signature.hs:52
+
+    // range / hole checks: first non-zero scalar outside what the SRS holds, per MSM
+    const uint32_t nm = (uint32_t)pm.size();
+    uint32_t* viol = ar.get<uint32_t>(3 * (size_t)nm);
+    SONIC_CUDA(cudaMemsetAsync(viol, 0xff, 12 * (size_t)nm, st));
+    std::vector<MsmJob> jobs(nm);
+    struct Rng { int64_t a, b; };
+    std::vector<Rng> rngs(3 * (size_t)nm, Rng{0, 0});
+    for (uint32_t i = 0; i < nm; ++i) {
+        const ProofMsm& m = pm[i];
+        const int64_t lo = m.lo, hi = m.lo + (int64_t)m.len;
+        Rng* r = &rngs[3 * (size_t)i];
+        if (lo < -d) r[0] = {lo, std::min(hi, -d)};
+        if (m.family == SONIC_FAMILY_ALPHA && lo <= 0 && 0 < hi) r[1] = {0, 1};
+        if (hi > d + 1) r[2] = {std::max(lo, d + 1), hi};
+        for (int k = 0; k < 3; ++k) {
+            if (r[k].b > r[k].a) {
+                const uint32_t a = (uint32_t)(r[k].a - lo), b = (uint32_t)(r[k].b - lo);
+                SONIC_LAUNCH(k_first_nonzero_job, div_up(b - a, 256), 256, 0, m.scal, a, b, viol + 3 * (size_t)i + k);
+            }
+        }
+        const int64_t clo = std::max(lo, -d), chi = std::max(clo, std::min(hi, d + 1));
+        jobs[i].point_base = (uint32_t)srs->index(m.family, clo);
+        jobs[i].n = (uint32_t)(chi - clo);
+        // scalar_off is relative to one base pointer: use the arena base of the first job
+        jobs[i].scalar_off = 0;
+        jobs[i].pad = 0;
+    }
+    // all scalar vectors live in the arena; express them as offsets from the lowest address
+    const Fr* sbase = pm[0].scal;
+    for (const ProofMsm& m : pm) if (m.scal < sbase) sbase = m.scal;
+    for (uint32_t i = 0; i < nm; ++i) {
+        const int64_t clo = std::max(pm[i].lo, -d);
+        jobs[i].scalar_off = (uint32_t)((pm[i].scal - sbase) + (clo - pm[i].lo));
+    }
+    G1Affine* d_aff = ar.get<G1Affine>(nm);
+    uint8_t* d_comp = ar.get<uint8_t>((size_t)nm * 48);
+    for (uint32_t first = 0; first < nm; first += MSM_MAX_JOBS) {
+        const uint32_t cnt = std::min<uint32_t>(MSM_MAX_JOBS, nm - first);
+        std::vector<MsmJob> part(jobs.begin() + first, jobs.begin() + first + cnt);
+        msm_run(cx, srs->points, (const uint32_t*)sbase, part, d_aff + first, d_comp + (size_t)first * 48);
+    }
+
+    // ---- results to the host ---------------------------------------------------------------------
+    std::vector<uint8_t> h_comp((size_t)nm * 48);
+    std::vector<Fr> h_vals(nvals ? nvals : 1);
+    std::vector<uint32_t> h_viol(3 * (size_t)nm);
+    std::vector<Fr> h_rnd(nr);
+    uint32_t h_bad = 0;
+    SONIC_CUDA(cudaMemcpyAsync(h_comp.data(), d_comp, h_comp.size(), cudaMemcpyDeviceToHost, st));
+    SONIC_CUDA(cudaMemcpyAsync(h_vals.data(), vals, nvals * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+    SONIC_CUDA(cudaMemcpyAsync(h_viol.data(), viol, h_viol.size() * 4, cudaMemcpyDeviceToHost, st));
+    SONIC_CUDA(cudaMemcpyAsync(h_rnd.data(), d_rnd, nr * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+    SONIC_CUDA(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, st));
+    SONIC_CUDA(cudaStreamSynchronize(st));
+    msm_collect_timing(cx);
+    {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, cx.ev[4], cx.ev[5]) == cudaSuccess) cx.timing_ms["poly"] = ms;
+    }
+    if (h_bad) return fail(SONIC_ERR_NONCANONICAL, "an Fr encoding is not a canonical residue (>= r)");
+    for (uint32_t i = 0; i < nm; ++i)
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t v = h_viol[3 * (size_t)i + k];
+            if (v == 0xffffffffu) continue;
+            const int64_t e = pm[i].lo + (int64_t)v;
+            const uint64_t dd = srs->d;
+            if (pm[i].commit_text) {
+                if (e > 0) return fail(SONIC_ERR_SRS_TOO_SHORT, "commitPoly: gPositiveAlphaX is not long enough: %lld >= %llu", (long long)(e - 1), (unsigned long long)dd);
+                return fail(SONIC_ERR_SRS_TOO_SHORT, "commitPoly: gNegativeAlphaX is not long enough: %lld >= %llu", (long long)((e < 0 ? -e : e) - 1), (unsigned long long)dd);
+            }
+            if (e >= 0) return fail(SONIC_ERR_SRS_TOO_SHORT, "openPoly: gPositiveX is not long enough: %lld >= %llu", (long long)e, (unsigned long long)(dd + 1));
+            return fail(SONIC_ERR_SRS_TOO_SHORT, "openPoly: gNegativeX is not long enough: %lld >= %llu", (long long)(-e - 1), (unsigned long long)dd);
+        }
+
+    // ---- proof bytes in record order (Protocol.hs:28-38, Signature.hs:22-29) ---------------------
+    uint8_t* o = out;
+    uint32_t g = 0;
+    auto putG = [&]() { memcpy(o, h_comp.data() + (size_t)g * 48, 48); o += 48; ++g; };
+    auto putF = [&](const Fr& v) { memcpy(o, v.l, 32); o += 32; };
+    if (has_main) {
+        putG();               // prR
+        putG();               // prT
+        putF(h_vals[v_a]);    // prA
+        putG();               // prWa
+        putF(h_vals[v_b]);    // prB
+        putG();               // prWb
+        putG();               // prWt
+        putF(h_vals[v_s]);    // prS
+    }
+    for (uint32_t j = 0; j < M; ++j) { putG(); putF(h_vals[v_sj[j]]); putG(); }     // (S_j, (s_j, W_j))
+    for (uint32_t j = 0; j < M; ++j) { putF(h_vals[v_spj[j]]); putG(); putG(); }    // (s'_j, W'_j, Q_j)
+    putG();                        // hscQv
+    putG();                        // hscC
+    putF(h_rnd[6 + 2 * M]);        // hscU
+    putF(h_rnd[7 + 2 * M]);        // hscV
+    (void)v_t; (void)v_qv; (void)v_wpj;
+    return SONIC_OK;
+}
+
+}  // namespace sonic

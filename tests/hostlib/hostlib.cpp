@@ -1,0 +1,70 @@
+// Host build of the device arithmetic headers (portable carry-chain emulation) so that
+// the exact limb algorithms can be checked against the big-int oracle without a GPU.
+// TEST INFRASTRUCTURE ONLY: the product library never links this file.
+#include <cstring>
+#include "../../sonic_b200/csrc/g1.cuh"
+#include "../../sonic_b200/csrc/scalar.cuh"
+
+using namespace sonic;
+
+template <class F> static F ld(const uint32_t* p) { F r; memcpy(r.l, p, sizeof(r.l)); return r; }
+template <class F> static void st(uint32_t* p, const F& v) { memcpy(p, v.l, sizeof(v.l)); }
+
+extern "C" {
+// op: 0 mul, 1 add, 2 sub, 3 to_mont(a), 4 from_mont(a), 5 inv(a), 6 sqr(a), 7 neg(a)
+void ht_fq_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    Fq x = ld<Fq>(a), y = ld<Fq>(b), r;
+    switch (op) {
+        case 0: r = fp_mul(x, y); break;
+        case 1: r = fp_add(x, y); break;
+        case 2: r = fp_sub(x, y); break;
+        case 3: r = fp_to_mont(x); break;
+        case 4: r = fp_from_mont(x); break;
+        case 5: r = fp_inv(x); break;
+        case 6: r = fp_sqr(x); break;
+        default: r = fp_neg(x); break;
+    }
+    st(out, r);
+}
+void ht_fr_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    Fr x = ld<Fr>(a), y = ld<Fr>(b), r;
+    switch (op) {
+        case 0: r = fp_mul(x, y); break;
+        case 1: r = fp_add(x, y); break;
+        case 2: r = fp_sub(x, y); break;
+        case 3: r = fp_to_mont(x); break;
+        case 4: r = fp_from_mont(x); break;
+        case 5: r = fp_inv(x); break;
+        case 6: r = fp_sqr(x); break;
+        default: r = fp_neg(x); break;
+    }
+    st(out, r);
+}
+static G1XYZZ ldx(const uint32_t* p) { G1XYZZ r; r.x = ld<Fq>(p); r.y = ld<Fq>(p + 12); r.zz = ld<Fq>(p + 24); r.zzz = ld<Fq>(p + 36); return r; }
+static void stx(uint32_t* p, const G1XYZZ& r) { st(p, r.x); st(p + 12, r.y); st(p + 24, r.zz); st(p + 36, r.zzz); }
+static G1Affine lda(const uint32_t* p) { G1Affine r; r.x = ld<Fq>(p); r.y = ld<Fq>(p + 12); return r; }
+static void sta(uint32_t* p, const G1Affine& r) { st(p, r.x); st(p + 12, r.y); }
+
+// all points in Montgomery form. op: 0 madd(acc, aff b), 1 add(acc, xyzz b), 2 dbl(acc), 3 mdbl(aff a -> xyzz)
+void ht_g1_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    G1XYZZ r;
+    switch (op) {
+        case 0: r = ldx(a); g1_madd(r, lda(b)); break;
+        case 1: r = ldx(a); g1_add(r, ldx(b)); break;
+        case 2: r = g1_dbl(ldx(a)); break;
+        default: r = g1_mdbl(lda(a)); break;
+    }
+    stx(out, r);
+}
+void ht_g1_to_affine(const uint32_t* a, uint32_t* out) { sta(out, g1_to_affine(ldx(a))); }
+void ht_g1_compress(const uint32_t* aff, uint8_t* out48) { g1_compress(lda(aff), out48); }
+void ht_g1_gen(uint32_t* out) { sta(out, G1Affine::gen()); }
+
+// signed-digit recoding of a canonical scalar: returns W digits
+int ht_recode(const uint32_t* scalar8, int c, int32_t* digits) {
+    ScalarDigits sd(scalar8, c);
+    int W = msm_num_windows(c);
+    for (int j = 0; j < W; ++j) digits[j] = sd.next();
+    return W;
+}
+}

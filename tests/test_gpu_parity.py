@@ -1,0 +1,230 @@
+"""GPU parity: SRS.new, commitPoly, openPoly, msm, prove and hscProve through the C ABI
+against the CPU oracle on the same seeded inputs.  Byte-exact."""
+import random
+
+import pytest
+
+from oracle import bls12_381 as bls
+from oracle import sonic as S
+from tests.util import example1, example2, random_d, rnd_circuit, to_gpu_types
+
+pytestmark = pytest.mark.gpu
+R = bls.R
+C = bls.g1_compress
+
+
+def _srs_pair(sb, d, x, alpha):
+    return sb.SRS.new(d, x, alpha), S.srs_new(d, x, alpha)
+
+
+def test_srs_new_matches_reference_vectors(gpu):
+    rng = random.Random(11)
+    for d in (1, 2, 7, 33, 130):
+        x, alpha = rng.randrange(1, R), rng.randrange(R)
+        g, o = _srs_pair(gpu, d, x, alpha)
+        assert g.gNegativeX == [C(p) for p in o.gNegativeX]
+        assert g.gPositiveX == [C(p) for p in o.gPositiveX]
+        assert g.gNegativeAlphaX == [C(p) for p in o.gNegativeAlphaX]
+        assert g.gPositiveAlphaX == [C(p) for p in o.gPositiveAlphaX]
+
+
+def test_srs_degenerate_trapdoors(gpu):
+    # bench/Main.hs:23 uses x = 1 (every base equals g or g^alpha); alpha = 0 makes a family infinity
+    for x, alpha in ((1, 4), (R - 1, 1), (5, 0)):
+        g, o = _srs_pair(gpu, 9, x, alpha)
+        assert g.gPositiveX == [C(p) for p in o.gPositiveX]
+        assert g.gNegativeAlphaX == [C(p) for p in o.gNegativeAlphaX]
+    with pytest.raises(gpu.SonicError) as e:
+        gpu.SRS.new(4, 0, 3)
+    assert e.value.kind == "DIV_BY_ZERO"
+    with pytest.raises(gpu.SonicError) as e:
+        g.g1(1, 0)  # g^alpha is not part of the SRS (SRS.hs:38)
+    assert e.value.kind == "SRS_TOO_SHORT"
+
+
+def _rand_laurent(rng, lo, hi, density=0.8):
+    f = {e: rng.randrange(R) for e in range(lo, hi + 1) if rng.random() < density}
+    return f
+
+
+def test_commit_open_small_vs_oracle(gpu):
+    rng = random.Random(12)
+    for trial in range(6):
+        d = rng.randint(20, 60)
+        x, alpha = (1, 4) if trial == 0 else (rng.randrange(1, R), rng.randrange(1, R))
+        g, o = _srs_pair(gpu, d, x, alpha)
+        maxm = rng.randint(5, d)
+        f = _rand_laurent(rng, -maxm, maxm)  # shifted by d - max: stays inside [-d, d]
+        f.pop(-(d - maxm), None)  # shifted exponent 0 is the alpha hole
+        assert gpu.commitPoly(g, maxm, f) == C(S.commitPoly(o, maxm, f))
+        z = rng.randrange(1, R)
+        v, w = gpu.openPoly(g, z, f)
+        ov, ow = S.openPoly(o, z, f)
+        assert (v, w) == (ov, C(ow))
+        assert S.pcV_trapdoor(o, maxm, bls.g1_decompress(gpu.commitPoly(g, maxm, f)), z, (v, bls.g1_decompress(w)))
+
+
+def test_commit_open_edge_cases(gpu):
+    rng = random.Random(13)
+    d = 24
+    x, alpha = rng.randrange(1, R), rng.randrange(1, R)
+    g, o = _srs_pair(gpu, d, x, alpha)
+    # empty polynomial, constants, single terms, small coefficients (+-1, as in Constraints.hs:45)
+    cases = [{}, {3: 0}, {0: 5}, {1: 1}, {-1: R - 1}, {-d: 7, d: 9}, {k: 1 for k in range(-d, d + 1) if k},
+             {k: R - 1 for k in range(-5, 6)}]
+    for f in cases:
+        z = rng.randrange(1, R)
+        v, w = gpu.openPoly(g, z, f)
+        ov, ow = S.openPoly(o, z, f)
+        assert (v, w) == (ov, C(ow)), f
+    for f in cases:
+        if any(e == 0 and c % R for e, c in f.items()):
+            continue
+        assert gpu.commitPoly(g, d, f) == C(S.commitPoly(o, d, f)), f
+    # panics of `index` (CommitmentScheme.hs:70-73), text included
+    for maxm, f in ((d, {0: 1}), (d, {d + 1: 1}), (d, {-d - 1: 2, 3: 1}), (d - 3, {d: 1})):
+        with pytest.raises(S.SonicPanic) as oe:
+            S.commitPoly(o, maxm, f)
+        with pytest.raises(gpu.SonicError) as ge:
+            gpu.commitPoly(g, maxm, f)
+        assert ge.value.kind == "SRS_TOO_SHORT" and ge.value.text == str(oe.value)
+    for f in ({d + 2: 1}, {-d - 2: 1, 0: 3}):
+        with pytest.raises(S.SonicPanic) as oe:
+            S.openPoly(o, 5, f)
+        with pytest.raises(gpu.SonicError) as ge:
+            gpu.openPoly(g, 5, f)
+        assert ge.value.text == str(oe.value)
+    # z = 0: fine without negative powers, `recip 0` with them
+    assert gpu.openPoly(g, 0, {0: 4, 2: 9}) == (4, C(S.openPoly(o, 0, {0: 4, 2: 9})[1]))
+    with pytest.raises(gpu.SonicError) as ge:
+        gpu.openPoly(g, 0, {-1: 4, 2: 9})
+    assert ge.value.kind == "DIV_BY_ZERO"
+
+
+def test_msm_sizes_and_windows_vs_trapdoor(gpu):
+    """MSM of N points against the trapdoor identity  sum_k s_k g^{x^k} = g^{sum_k s_k x^k}
+    (one Fr evaluation + one scalar multiplication on the CPU checks an MSM of any size)."""
+    rng = random.Random(14)
+    d = 3000
+    x, alpha = rng.randrange(1, R), rng.randrange(1, R)
+    g = gpu.SRS.new(d, x, alpha)
+    xi = pow(x, -1, R)
+    try:
+        for N, wb, chunk in ((1, 0, 0), (2, 4, 8), (257, 7, 0), (1000, 0, 0), (4097, 11, 16), (6001, 13, 64), (6001, 16, 0)):
+            gpu.set_option("window_bits", wb)
+            gpu.set_option("chunk", chunk)
+            lo = -(N // 2)
+            sc = [rng.randrange(R) for _ in range(N)]
+            for fam, mult in ((0, 1), (1, alpha)):
+                s = list(sc)
+                if fam == 1 and lo <= 0 < lo + N:
+                    s[-lo] = 0
+                acc = 0
+                for k, v in enumerate(s):
+                    e = lo + k
+                    acc += v * (pow(x, e, R) if e >= 0 else pow(xi, -e, R))
+                want = C(bls.g1_mul_gen(acc * mult % R))
+                assert gpu.msm(g, fam, lo, s) == want, (N, wb, fam)
+    finally:
+        gpu.set_option("window_bits", 0)
+        gpu.set_option("chunk", 0)
+
+
+def test_msm_skewed_and_degenerate(gpu):
+    """Zeros, +-1 and repeated scalars (heavy buckets), and x = 1 where every base coincides."""
+    rng = random.Random(15)
+    for x in (1, rng.randrange(2, R)):
+        d = 2500
+        g = gpu.SRS.new(d, x, 4)
+        N = 5000
+        pool = [0, 0, 0, 0, 1, R - 1, 2, rng.randrange(R)]
+        s = [rng.choice(pool) for _ in range(N)]
+        lo = -d
+        xi = pow(x, -1, R)
+        acc = sum(v * (pow(x, lo + k, R) if lo + k >= 0 else pow(xi, -(lo + k), R)) for k, v in enumerate(s)) % R
+        for wb in (0, 8, 14):
+            gpu.set_option("window_bits", wb)
+            assert gpu.msm(g, 0, lo, s) == C(bls.g1_mul_gen(acc)), (x, wb)
+        gpu.set_option("window_bits", 0)
+        # sharded: partial sums of two slices fold to the same element
+        parts = [gpu.msm_partial(g, 0, lo, s[:1234]), gpu.msm_partial(g, 0, lo + 1234, s[1234:])]
+        assert gpu.g1_sum(parts) == C(bls.g1_mul_gen(acc))
+
+
+@pytest.mark.parametrize("which", ["example1", "example2"])
+def test_prove_reference_circuits_byte_exact(gpu, which):
+    rng = random.Random(16)
+    circuit, assignment = example1() if which == "example1" else example2(12)
+    n, Q = len(assignment.aL), len(circuit.weights.wL)
+    gc, ga = to_gpu_types(gpu, circuit, assignment)
+    for d in ((12, 25) if n == 1 else (16, 50)):
+        x, alpha = rng.randrange(1, R), rng.randrange(1, R)
+        g, o = _srs_pair(gpu, d, x, alpha)
+        rnd = [rng.randrange(1, R) for _ in range(S.rnd_count(Q))]
+        want, (y, z, yzs) = S.prove(o, assignment, circuit, rnd)
+        got = gpu.prove_bytes(g, ga, gc, rnd)
+        assert got == S.encode_proof(want)
+        assert S.verify_trapdoor(o, circuit, S.decode_proof(got, Q), y, z, yzs)
+
+
+def test_prove_random_circuits_like_test_sonic(gpu):
+    """test/Test/Protocol.hs:14-23 `test_sonic`, on the CUDA path, checked byte for byte against
+    the oracle and then by `verify` (trapdoor form)."""
+    rng = random.Random(17)
+    for trial in range(6):
+        circuit, assignment = rnd_circuit(rng, n=rng.randint(1, 12))
+        n, Q = len(assignment.aL), len(circuit.weights.wL)
+        d = max(random_d(rng, n), 4 * n + 8)
+        x, alpha = rng.randrange(1, R), rng.randrange(1, R)
+        g, o = _srs_pair(gpu, d, x, alpha)
+        gc, ga = to_gpu_types(gpu, circuit, assignment)
+        rnd = [rng.randrange(1, R) for _ in range(S.rnd_count(Q))]
+        want, (y, z, yzs) = S.prove_dense(o, assignment, circuit, rnd)
+        got = gpu.prove_bytes(g, ga, gc, rnd)
+        assert got == S.encode_proof(want), (trial, n, Q, d)
+        assert S.verify_trapdoor(o, circuit, S.decode_proof(got, Q), y, z, yzs)
+
+
+def test_prove_panics_like_the_reference(gpu):
+    rng = random.Random(18)
+    circuit, assignment = example2(12)
+    gc, ga = to_gpu_types(gpu, circuit, assignment)
+    rnd = [rng.randrange(1, R) for _ in range(S.rnd_count(5))]
+    x, alpha = rng.randrange(1, R), rng.randrange(1, R)
+    for d in (13, 15):  # 13 < 7n: Protocol.hs:54-55; 15 < 4n+8: commitPoly runs off the SRS
+        g, o = _srs_pair(gpu, d, x, alpha)
+        with pytest.raises(S.SonicPanic) as oe:
+            S.prove(o, assignment, circuit, rnd)
+        with pytest.raises(gpu.SonicError) as ge:
+            gpu.prove_bytes(g, ga, gc, rnd)
+        assert ge.value.text == str(oe.value)
+    # an unsatisfied circuit leaves a non-zero X^0 term in t(X,y): commitPoly indexes g^alpha and panics
+    g, o = _srs_pair(gpu, 40, x, alpha)
+    bad = S.Assignment(list(assignment.aL), list(assignment.aR), [assignment.aO[0] + 1, assignment.aO[1]])
+    with pytest.raises(S.SonicPanic) as oe:
+        S.prove(o, bad, circuit, rnd)
+    with pytest.raises(gpu.SonicError) as ge:
+        gpu.prove_bytes(g, gpu.Assignment(bad.aL, bad.aR, bad.aO), gc, rnd)
+    assert ge.value.text == str(oe.value)
+
+
+def test_hsc_prove_vs_oracle(gpu):
+    """test/Test/Signature.hs:20-36."""
+    rng = random.Random(19)
+    for trial in range(3):
+        circuit, assignment = rnd_circuit(rng, n=rng.randint(2, 9))
+        n, Q = len(assignment.aL), len(circuit.weights.wL)
+        d = random_d(rng, n)
+        x, alpha = rng.randrange(1, R), rng.randrange(1, R)
+        g, o = _srs_pair(gpu, d, x, alpha)
+        gc, _ = to_gpu_types(gpu, circuit, assignment)
+        m = Q if trial else Q + 2
+        yzs = [(rng.randrange(1, R), rng.randrange(1, R)) for _ in range(m)]
+        u, v = rng.randrange(1, R), rng.randrange(1, R)
+        sXY = S.sPoly(circuit.weights)
+        want = S.hscProve(o, sXY, yzs, u, v)
+        got = gpu.hscProve(g, gc, yzs, u, v)
+        assert [(a, (b, c)) for a, (b, c) in got.hscS] == [(C(a), (b, C(c))) for a, (b, c) in want.hscS]
+        assert got.hscW == [(a, C(b), C(c)) for a, b, c in want.hscW]
+        assert (got.hscQv, got.hscC, got.hscU, got.hscV) == (C(want.hscQv), C(want.hscC), u, v)
+        assert S.hscVerify_trapdoor(o, sXY, yzs, want)
