@@ -94,6 +94,9 @@ def l_divide_linear(a: Laurent, z: int) -> Optional[Laurent]:
     exact division or Nothing."""
     if not a:
         return {}
+    if z % R == 0:
+        # the divisor [(0,-0),(1,1)] normalises to the monomial X: Laurent division shifts offsets
+        return {e - 1: c for e, c in a.items()}
     lo, hi = min(a), max(a)
     # a = X^lo * g(X), g an ordinary polynomial of degree hi-lo
     g = [a.get(lo + k, 0) for k in range(hi - lo + 1)]
