@@ -1,0 +1,407 @@
+#!/usr/bin/env python3
+"""bench.py -- the Sonic prover hot path on N B200s (one process per GPU).
+
+A step is one prove() at BASELINE.json's headline configuration (config 4: synthetic circuit,
+n = 2^16 multiplication constraints, Q = 8 linear constraints, d = 7n, SRS resident in HBM).
+metric = G1 MSM Mpoints/s = MSM terms of one proof (4Q+7 = 39 commitments/openings) / step time;
+`prove_ms` (= ms_per_step) is reported alongside.
+
+  value     : inputs (assignment, draws) already resident in HBM when the timed region starts
+  e2e       : the same proofs through the public C ABI with HOST (pinned) buffers: host->device
+              copies of the assignment and device->host of the proof inside the timed region
+  roofline  : the bucket-accumulation kernel against the measured integer-multiply peak
+  N > 1     : one proof sharded over the ranks (contiguous slices of every MSM), one NCCL
+              all-gather of the 4Q+7 partial sums per proof; strong scaling
+
+`--impl reference` times the reference's CPU algorithm (one double-and-add scalar
+multiplication per term, CommitmentScheme.hs:26-29) as restated in oracle/csrc/sonic_ref.c
+-- the Haskell original cannot be built here (no GHC) -- on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CANON_WINDOW = 16                      # canonical c = 16 => W = 16 bucket insertions / point
+LMAC_PER_MADD = 3000                   # 10 Fq multiplications x 300 LMAC
+CANON_LMAC_PER_POINT = 16 * LMAC_PER_MADD
+
+
+def msm_terms_per_proof(n: int, Q: int) -> int:
+    """Terms of the 4Q+7 MSMs of one proof (A3/A4 sizes)."""
+    r, t, s, c = 3 * n + 5, 7 * n + 9, 3 * n + 1, 2 * n + Q + 1
+    main = r + t + 2 * (r - 1) + (t - 1)
+    hsc = Q * (s + (s - 1)) + Q * ((s - 1) + (c - 1)) + (c - 1) + c
+    return main + hsc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+_TABLES = {}
+
+
+def cpu_sample(sample_terms: int, threads: int, seed: int):
+    """Reference-algorithm MSM on `sample_terms` terms of the workload's distribution (uniform Fr
+    coefficients against SRS bases g^{x^k} of the same trapdoor).  Returns (points_per_s, seconds)."""
+    from oracle import cref
+    from sonic_b200 import synth
+
+    x, alpha = synth.trapdoor()
+    d = sample_terms // 2
+    if d not in _TABLES:                                                 # setup, not timed
+        _TABLES[d] = cref.srs_new(d, x, alpha, threads=host_threads())
+    pts = _TABLES[d][:96 * sample_terms]                                 # plain family, exponents -d ..
+    scal = synth.fr_bytes_fast(seed, sample_terms).tobytes()
+    t0 = time.perf_counter()
+    cref.msm_naive(pts, scal, sample_terms, threads)
+    dt = time.perf_counter() - t0
+    return sample_terms / dt, dt
+
+
+def run_reference(args, rank: int, world: int) -> None:
+    """`--impl reference`: rank 0 alone times the CPU restatement; other ranks exit 0."""
+    if rank != 0:
+        return
+    n, Q = 1 << args.log_n, args.Q
+    threads = host_threads()
+    sample = threads * 2048
+    for _ in range(args.warmup):
+        cpu_sample(sample, threads, 99)
+    times = []
+    for s in range(args.steps):
+        _, dt = cpu_sample(sample, threads, 100 + s)
+        times.append(dt)
+    value = sample * len(times) / sum(times) / 1e6
+    terms = msm_terms_per_proof(n, Q)
+    line = {
+        "impl": "reference", "metric": "G1 MSM Mpoints/s inside prove() at n=2^%d" % args.log_n, "value": value,
+        "unit": "Mpoints/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "prove() n=2^%d Q=%d d=7n: MSM terms of one proof = %d; each step = reference-algorithm MSM "
+                               "(double-and-add per term, CommitmentScheme.hs:26-29) on a %d-term sample" % (args.log_n, Q, terms, sample),
+                   "extrapolated_prove_ms": 1e3 * terms / (value * 1e6)},
+        "cpu_baseline": {"value": value, "unit": "Mpoints/s", "cores": threads, "kind": "port",
+                         "sample": "%d uniform-Fr terms against SRS bases of the bench trapdoor, %d threads; C restatement "
+                                   "(oracle/csrc/sonic_ref.c) -- the Haskell reference cannot be built here (no GHC)" % (sample, threads)},
+        "e2e": {"value": value, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", type=int, default=16, help="log2 of the number of multiplication constraints")
+    ap.add_argument("--Q", type=int, default=8)
+    ap.add_argument("--no-sweep", action="store_true", help="skip the standalone MSM sweep (config 3)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sweep-max", type=int, default=24)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import sonic_b200 as sb
+    from sonic_b200 import capi, synth
+    from sonic_b200 import dist as sdist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sb.init(local_rank)
+    L = capi.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- roofline denominator: measured integer-multiply peak on this device ---------------------
+    peaks = [L.sonic_imad_peak_lmacs(v, 3000) for v in (0, 1, 2)]
+    imad_peak = max(peaks)
+
+    # ---- workload -----------------------------------------------------------------------------------
+    n, Q = 1 << args.log_n, args.Q
+    d = 7 * n
+    x, alpha = synth.trapdoor()
+    t0 = time.perf_counter()
+    srs = sb.SRS.new(d, x, alpha)
+    srs_new_wall_ms = 1e3 * (time.perf_counter() - t0)
+    srs_new_dev_ms = sb.last_timing_ms("total")
+    circ = synth.synthetic_circuit_bytes(n, Q, seed=4)
+    ch = ctypes.c_void_p()
+    capi.check(L.sonic_circuit_load(n, Q, circ["wL"].ctypes.data, circ["wR"].ctypes.data, circ["wO"].ctypes.data,
+                                    circ["cs"].ctypes.data, ctypes.byref(ch)))
+    nr = 2 * Q + 8
+    rnd_ints = [v or 1 for v in synth.fr_ints(40, nr)]
+    # pinned host buffers (what the Haskell shim would hand over) and device-resident copies
+    host_in = torch.empty(3 * n * 32, dtype=torch.uint8).pin_memory()
+    host_in.numpy()[:] = np.concatenate([circ["aL"], circ["aR"], circ["aO"]])
+    host_rnd = torch.empty(nr * 32, dtype=torch.uint8).pin_memory()
+    host_rnd.numpy()[:] = np.frombuffer(synth.ints_to_bytes(rnd_ints), dtype=np.uint8)
+    hin, hrnd = host_in.data_ptr(), host_rnd.data_ptr()
+    d_in, d_rnd = ctypes.c_void_p(), ctypes.c_void_p()
+    capi.check(L.sonic_dev_alloc(3 * n * 32, ctypes.byref(d_in)))
+    capi.check(L.sonic_dev_alloc(nr * 32, ctypes.byref(d_rnd)))
+    capi.check(L.sonic_dev_upload(d_in, hin, 3 * n * 32))
+    capi.check(L.sonic_dev_upload(d_rnd, hrnd, nr * 32))
+    proof_size = int(L.sonic_proof_size(Q))
+    blob_size = int(L.sonic_shard_blob_size(Q))
+    out = ctypes.create_string_buffer(max(proof_size, blob_size))
+    written = ctypes.c_uint64(0)
+    terms = msm_terms_per_proof(n, Q)
+
+    def gather_and_combine(blob: bytes) -> bytes:
+        blobs = sdist.all_gather_bytes(blob)
+        proof = ctypes.create_string_buffer(proof_size)
+        capi.check(L.sonic_prove_combine(Q, world, b"".join(blobs), proof, proof_size, ctypes.byref(written)))
+        return proof.raw
+
+    def step_resident() -> bytes:
+        capi.check(L.sonic_prove_shard_device(srs._h, ch, d_in, d_rnd, hrnd, rank, world, out, len(out), ctypes.byref(written)))
+        if world == 1:
+            return out.raw[:proof_size]
+        return gather_and_combine(out.raw[:blob_size])
+
+    def step_e2e() -> bytes:
+        if world == 1:
+            capi.check(L.sonic_prove(srs._h, ch, hin, hin + n * 32, hin + 2 * n * 32, hrnd, out, len(out), ctypes.byref(written)))
+            return out.raw[:proof_size]
+        capi.check(L.sonic_prove_shard(srs._h, ch, hin, hin + n * 32, hin + 2 * n * 32, hrnd, rank, world, out, len(out), ctypes.byref(written)))
+        return gather_and_combine(out.raw[:blob_size])
+
+    def timed(step, steps):
+        barrier()
+        launches0 = sb.launch_count()
+        capi.check(L.sonic_bench_mark(0))
+        w0 = time.perf_counter()
+        proof = None
+        for _ in range(steps):
+            proof = step()
+        capi.check(L.sonic_bench_mark(1))
+        ev_ms = L.sonic_bench_elapsed_ms(0, 1)
+        torch.cuda.synchronize()
+        wall_ms = 1e3 * (time.perf_counter() - w0)
+        barrier()
+        return max_over_ranks(ev_ms), max_over_ranks(wall_ms), sb.launch_count() - launches0, proof
+
+    sampler = ClockSampler(local_rank)   # started before the warm-up so that NVML start-up is not in the timed region
+    sampler.start()
+    for _ in range(args.warmup):
+        p_res = step_resident()
+    for _ in range(args.warmup):
+        p_e2e = step_e2e()
+    if p_res != p_e2e:
+        raise SystemExit("resident and host-buffer proofs differ")
+    ev_ms, wall_ms, launches, proof = timed(step_resident, args.steps)
+    stage = {k: sb.last_timing_ms(k) for k in ("msm", "msm.sort", "msm.accumulate", "msm.accumulate_kernel", "msm.reduce", "poly", "total",
+                                               "msm.window_bits", "msm.windows", "msm.terms", "msm.entries", "msm.chunk", "msm.buckets")}
+    e2e_ev_ms, e2e_wall_ms, _, proof2 = timed(step_e2e, args.steps)
+    clocks = sampler.stop()
+    if proof != proof2 or proof != p_res:
+        raise SystemExit("proofs differ between steps")
+    ms_per_step = ev_ms / args.steps
+    e2e_ms_per_step = e2e_ev_ms / args.steps
+    value = terms / (ms_per_step * 1e-3) / 1e6
+    e2e_value = terms / (e2e_ms_per_step * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (bucket accumulation), from the last timed step ----------
+    acc_ms = stage["msm.accumulate_kernel"]
+    shard_terms = stage["msm.terms"]                       # terms this rank's launch processed
+    canon_lmac = shard_terms * CANON_LMAC_PER_POINT
+    exec_lmac = stage["msm.entries"] * LMAC_PER_MADD
+    achieved = canon_lmac / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_accumulate_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+    except Exception:
+        pass
+    roofline = {
+        "bound": "imad", "kernel": "k_msm_accumulate", "achieved": achieved, "peak": imad_peak / 1e12, "unit": "TLMAC/s",
+        "frac": achieved / (imad_peak / 1e12) if imad_peak else None, "traffic": traffic,
+        "note": "integer-multiply roofline (SURVEY.md 8d): achieved = canonical LMAC (terms x ceil(255/16) x 3000) / kernel time; "
+                "peak = max of three register-only IMAD microbenchmarks measured in this run (of measured)",
+        "executed": {"tlmac_per_s": exec_lmac / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else 0.0,
+                     "frac": (exec_lmac / (acc_ms * 1e-3)) / imad_peak if acc_ms > 0 and imad_peak else None,
+                     "window_bits": stage["msm.window_bits"], "windows": stage["msm.windows"], "entries": stage["msm.entries"]},
+        "kernel_ms": acc_ms, "msm_ms": stage["msm"], "kernel_share_of_step": acc_ms / ms_per_step if ms_per_step else None,
+        "whole_msm_frac": (canon_lmac / (stage["msm"] * 1e-3)) / imad_peak if stage["msm"] > 0 and imad_peak else None,
+        "imad_microbench_lmacs": {"mad.lo.cc+madc.hi": peaks[0], "mad.wide.u32": peaks[1], "mad.lo+mad.hi": peaks[2]},
+        "hbm": {"algorithmic_gb_per_s": stage["msm.entries"] * 100.0 / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None,
+                "peak_gb_per_s": hbm_peak, "note": "96 B base + 4 B entry per insertion; not the bound"},
+    }
+
+    # ---- standalone MSM sweep (config 3), scalars resident in HBM ----------------------------------
+    sweep = []
+    if not args.no_sweep:
+        top = max(16, min(args.sweep_max, 24))
+        dd = 1 << (top - 1)
+        big = srs if dd <= d else sb.SRS.new(dd, x, alpha)
+        for logn in range(16, top + 1, 2):
+            N = 1 << logn
+            for kind in ("uniform", "skewed"):
+                if kind == "skewed" and logn not in (20, top):
+                    continue
+                sc = synth.fr_bytes_fast(logn, N) if kind == "uniform" else synth.skewed_fr_bytes(logn, N)
+                lo, hi = sdist.slice_bounds(-(N // 2), N // 2, rank, world)
+                part = np.ascontiguousarray(sc[lo + N // 2:hi + N // 2])
+                dsc = ctypes.c_void_p()
+                capi.check(L.sonic_dev_alloc(part.nbytes, ctypes.byref(dsc)))
+                capi.check(L.sonic_dev_upload(dsc, part.ctypes.data, part.nbytes))
+                o48 = ctypes.create_string_buffer(96)
+
+                def one():
+                    if world == 1:
+                        capi.check(L.sonic_msm_g1_device(big._h, 0, lo, hi - lo, dsc, o48))
+                        return o48.raw[:48]
+                    capi.check(L.sonic_msm_g1_device_partial(big._h, 0, lo, hi - lo, dsc, o48))
+                    parts = sdist.all_gather_bytes(o48.raw)
+                    return sb.g1_sum(parts)
+                for _ in range(2):
+                    one()
+                reps = 3
+                barrier()
+                capi.check(L.sonic_bench_mark(2))
+                for _ in range(reps):
+                    one()
+                capi.check(L.sonic_bench_mark(3))
+                ms = max_over_ranks(L.sonic_bench_elapsed_ms(2, 3)) / reps
+                barrier()
+                sweep.append({"log2_n": logn, "scalars": kind, "ms": ms, "mpoints_per_s": N / (ms * 1e-3) / 1e6,
+                              "frac_of_imad_peak": N * CANON_LMAC_PER_POINT / (ms * 1e-3) / imad_peak,
+                              "window_bits": sb.last_timing_ms("msm.window_bits")})
+                capi.check(L.sonic_dev_free(dsc))
+
+    # ---- CPU baseline (rank 0, N = 1 only): the reference algorithm on one core --------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample = 1 << 15
+        rate, dt = cpu_sample(sample, 1, 7)
+        cpu = {"value": rate / 1e6, "unit": "Mpoints/s", "cores": 1, "kind": "port",
+               "sample": "%d uniform-Fr terms, reference algorithm (double-and-add per term + fold, CommitmentScheme.hs:26-29) "
+                         "in C (oracle/csrc/sonic_ref.c), %.1f s; the Haskell reference is single-threaded and cannot be built here" % (sample, dt),
+               "extrapolated_prove_ms": 1e3 * terms / rate, "host_threads_available": host_threads()}
+
+    if rank == 0:
+        line = {
+            "metric": "G1 MSM Mpoints/s inside prove() at n=2^%d" % args.log_n, "value": value, "unit": "Mpoints/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "prove_ms": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "prove() on a synthetic circuit, n=2^%d mult constraints, Q=%d, d=7n=%d, SRS resident in HBM "
+                                   "(BASELINE.json config 4); %d MSM terms in %d MSMs per proof" % (args.log_n, Q, d, terms, 4 * Q + 7),
+                       "n": n, "Q": Q, "d": d, "msm_terms_per_proof": terms, "ntt_len": 1 << (7 * n + 9 - 1).bit_length(),
+                       "parallelism": "1 GPU" if world == 1 else "%d GPUs: every MSM cut into %d contiguous slices, 1 NCCL all-gather of %d B per rank per proof" % (world, world, blob_size),
+                       "l2": "inputs larger than L2: the resident SRS is %.0f MB and is gathered at random every step" % ((4 * d + 2) * 96 / 1e6),
+                       "srs_new_ms": {"wall": srs_new_wall_ms, "device": srs_new_dev_ms, "points": 4 * d + 1}},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Mpoints/s", "ms_per_step": e2e_ms_per_step, "wall_ms_per_step": e2e_wall_ms / args.steps,
+                    "h2d_bytes_per_step": 3 * n * 32 + nr * 32, "d2h_bytes_per_step": (proof_size if world == 1 else blob_size) + 3 * (4 * Q + 7) * 4 + nr * 32 + 4},
+            "gpu_launches": launches,
+            "wall_ms_per_step": wall_ms / args.steps,
+            "stages_ms_last_step": {k: stage[k] for k in ("poly", "msm.sort", "msm.accumulate", "msm.reduce", "msm", "total")},
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "msm_sweep": sweep,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -103,6 +103,9 @@ int sonic_g1_sum(const uint8_t* raw96, uint64_t n, uint8_t out[48]);
 int sonic_msm_g1_device(const sonic_srs* srs, int family, int64_t lo, uint64_t len,
                         const void* d_scalars32, uint8_t out[48]);
 
+int sonic_msm_g1_device_partial(const sonic_srs* srs, int family, int64_t lo, uint64_t len,
+                                const void* d_scalars32, uint8_t out_raw[96]);
+
 /* ArithCircuit{weights = GateWeights{wL,wR,wO}, cs}  (src/Sonic/Protocol.hs:53; layout of
  * src/Sonic/Constraints.hs:38-53): three dense Q x n row-major matrices of Fr and Q constants,
  * kept resident across proofs. */
@@ -125,6 +128,29 @@ int sonic_prove(const sonic_srs* srs, const sonic_circuit* circuit, const uint8_
                 const uint8_t* aR, const uint8_t* aO, const uint8_t* rnd, uint8_t* proof_out,
                 uint64_t cap, uint64_t* written);
 
+/* One proof sharded over `world` processes (one per GPU).  Every rank calls
+ * sonic_prove_shard with the same inputs: it runs the (small) Fr side in full and only its
+ * contiguous slice of every MSM, and returns a shard blob of sonic_shard_blob_size(Q) bytes
+ * (4Q+7 raw partial sums + the 2Q+5 field values).  The ranks exchange the blobs (one NCCL
+ * all-gather); sonic_prove_combine folds them (`<>` per commitment) into the proof bytes. */
+uint64_t sonic_shard_blob_size(uint64_t Q);
+int sonic_prove_shard(const sonic_srs* srs, const sonic_circuit* circuit, const uint8_t* aL,
+                      const uint8_t* aR, const uint8_t* aO, const uint8_t* rnd, uint32_t rank,
+                      uint32_t world, uint8_t* blob_out, uint64_t cap, uint64_t* written);
+int sonic_prove_combine(uint64_t Q, uint32_t world, const uint8_t* blobs, uint8_t* proof_out,
+                        uint64_t cap, uint64_t* written);
+
+/* Same proof, with the assignment (aL | aR | aO, 3n Fr, canonical) and the draws already
+ * resident in device memory; `rnd_host` is the host copy of the draws (zero checks, hscU/hscV).
+ * Used by bench.py to time the path without the host->device copy of the inputs. */
+int sonic_prove_device(const sonic_srs* srs, const sonic_circuit* circuit, const void* d_assignment,
+                       const void* d_rnd, const uint8_t* rnd_host, uint8_t* proof_out, uint64_t cap,
+                       uint64_t* written);
+
+int sonic_prove_shard_device(const sonic_srs* srs, const sonic_circuit* circuit, const void* d_assignment,
+                             const void* d_rnd, const uint8_t* rnd_host, uint32_t rank, uint32_t world,
+                             uint8_t* out, uint64_t cap, uint64_t* written);
+
 /* hscProve :: SRS -> BiVLaurent Fr -> [(Fr,Fr)] -> m HscProof   (src/Sonic/Signature.hs:32-72)
  * s(X,Y) is the circuit's; yzs = m pairs (y_j, z_j) interleaved; uv = the two draws u, v.
  * Output: Q x (S_j s_j W_j) | Q x (s'_j W'_j Q_j) | hscQv hscC hscU hscV. */
@@ -136,10 +162,17 @@ int sonic_hsc_prove(const sonic_srs* srs, const sonic_circuit* circuit, uint64_t
 /* option names: "window_bits" (0 = automatic), "chunk" (0 = automatic) */
 int sonic_set_option(const char* name, int64_t value);
 /* device time in milliseconds of the kernels of the last call, by stage name; returns 0
- * if unknown.  Stages: "msm", "msm.sort", "msm.accumulate", "msm.reduce", "poly", "total" */
+ * if unknown.  Stages: "msm", "msm.sort", "msm.accumulate", "msm.reduce", "msm.accumulate_kernel", "poly", "total";
+ * the same call also reports counters of the last MSM batch: "msm.window_bits", "msm.windows",
+ * "msm.terms", "msm.entries", "msm.jobs", "msm.chunk", "msm.buckets" */
 double sonic_last_timing_ms(const char* stage);
 /* number of kernel launches issued by this library since sonic_init */
 uint64_t sonic_launch_count(void);
+/* CUDA events on the library's own stream, for harnesses that time several calls as one
+ * region (torch.cuda.Event only sees torch's stream): record into slot 0..5, read the time
+ * between two recorded slots (synchronises on the later one). */
+int sonic_bench_mark(int slot);
+double sonic_bench_elapsed_ms(int from_slot, int to_slot);
 /* Register-only integer multiply-add microbenchmark: returns measured 32x32->64
  * multiply-accumulates per second on the bound device (the roofline denominator). */
 double sonic_imad_peak_lmacs(int variant, int iters);

@@ -75,7 +75,7 @@ static u64 add_n(u64* r, const u64* a, const u64* b, int n) {
     return carry;
 }
 /* Montgomery product (CIOS), n limbs */
-static void mont_mul(u64* r, const u64* a, const u64* b, const u64* m, u64 inv, int n) {
+static inline __attribute__((always_inline)) void mont_mul(u64* r, const u64* a, const u64* b, const u64* m, u64 inv, const int n) {
     u64 t[NQ + 2];
     memset(t, 0, sizeof t);
     for (int i = 0; i < n; ++i) {

@@ -689,3 +689,91 @@ def prove_dense(srs: SRS, assignment: Assignment, circuit: ArithCircuit, rnd: Se
     proof = Proof(commitR, commitT, a, wa, b, wb, wt, szy,
                   HscProof(ss, sW, qv, c, u, v))
     return proof, (y, z, list(zip(ys, zs)))
+
+
+# ======================================================================================
+# The proof as a list of MSMs (record order) -- used to emulate sharded proving in tests
+# ======================================================================================
+def prove_dense_plan(srs: SRS, assignment: Assignment, circuit: ArithCircuit, rnd: Sequence[int]):
+    """Returns (msms, fvals): msms = [(alpha_family, lo_exponent, scalars)] in the order the
+    proof record lists its G1 fields, fvals = the Fr fields in record order.  Folding every
+    MSM gives exactly `prove_dense`."""
+    n = len(assignment.aL)
+    m = len(circuit.weights.wL)
+    d = srs.srsD
+    rnd = [r % R for r in rnd]
+    w = circuit.weights
+
+    def quotient(f: Dense, z: int):
+        fz = f.eval(z)
+        g = list(f.c)
+        g[-f.lo] = (g[-f.lo] - fz) % R
+        q = [0] * (len(g) - 1)
+        carry = 0
+        for k in range(len(g) - 1, 0, -1):
+            carry = (g[k] + z * carry) % R
+            q[k - 1] = carry
+        return fz, (False, f.lo, q)
+
+    def commit(f: Dense, maxm: int):
+        return (True, f.lo + d - maxm, list(f.c))
+
+    rX1 = dense_rX1(assignment, rnd[0:4])
+    y, z = rnd[4], rnd[5]
+    ky = sum(k * fr_pow(y, n + 1 + q) for q, k in enumerate(circuit.cs)) % R
+    sXy = dense_sXy(w, y)
+    tXy = dense_tXy(rX1, sXy, y, ky)
+    ys, zs = rnd[6:6 + m], rnd[6 + m:6 + 2 * m]
+    u, v = rnd[6 + 2 * m], rnd[7 + 2 * m]
+    a, qa = quotient(rX1, z)
+    b, qb = quotient(rX1, y * z % R)
+    _, qt = quotient(tXy, z)
+    msms = [commit(rX1, n), commit(tXy, d), qa, qb, qt]
+    fvals = [a, b, sXy.eval(z)]
+    sj = [dense_sXy(w, yj) for yj in ys]
+    suY = dense_suY(w, u)
+    s_vals, sp_vals = [], []
+    for f, zj in zip(sj, zs):
+        val, q = quotient(f, zj)
+        msms += [commit(f, d), q]
+        s_vals.append(val)
+    for f, yj in zip(sj, ys):
+        _, q1 = quotient(f, u)
+        val, q2 = quotient(suY, yj)
+        msms += [q1, q2]
+        sp_vals.append(val)
+    _, qv = quotient(suY, v)
+    msms += [qv, commit(suY, d)]
+    fvals += s_vals + sp_vals + [u, v]
+    return msms, fvals
+
+
+def fold_msm(srs: SRS, msm, lo_clip: Optional[int] = None, hi_clip: Optional[int] = None):
+    """Sum of one planned MSM, optionally restricted to exponents in [lo_clip, hi_clip)."""
+    alpha_family, lo, scal = msm
+    pts, scs = [], []
+    for k, v in enumerate(scal):
+        e = lo + k
+        if lo_clip is not None and not (lo_clip <= e < hi_clip):
+            continue
+        if v:
+            pts.append(srs_base(srs, alpha_family, e))
+            scs.append(v)
+    return msm_pippenger(pts, scs)
+
+
+def assemble_proof_bytes(Q: int, g48: Sequence[bytes], fvals: Sequence[int]) -> bytes:
+    """Record-order interleaving of the 4Q+7 G1 encodings and 2Q+5 Fr values."""
+    g, f = list(g48), [bls.fr_to_bytes(v) for v in fvals]
+    out = [g[0], g[1], f[0], g[2], f[1], g[3], g[4], f[2]]
+    gi, fi = 5, 3
+    for _ in range(Q):
+        out += [g[gi], f[fi], g[gi + 1]]
+        gi += 2
+        fi += 1
+    for _ in range(Q):
+        out += [f[fi], g[gi], g[gi + 1]]
+        gi += 2
+        fi += 1
+    out += [g[gi], g[gi + 1], f[fi], f[fi + 1]]
+    return b"".join(out)

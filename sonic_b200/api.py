@@ -300,3 +300,24 @@ def hscProve(srs: SRS, circuit: ArithCircuit, yzs: Sequence[Tuple[int, int]], u:
     flat = _frs([x for pair in yzs for x in pair])
     check(lib().sonic_hsc_prove(srs._h, ch.h, m, flat, _frs([u, v]), out, size, ctypes.byref(written)))
     return _parse_hsc(out.raw, m)
+
+
+def prove_shard(srs: SRS, assignment: Assignment, circuit: ArithCircuit, rnd: Sequence[int], rank: int, world: int) -> bytes:
+    """This rank's share of one proof (sonic_prove_shard): raw partial sums + field values."""
+    ch = circuit.handle()
+    size = int(lib().sonic_shard_blob_size(ch.Q))
+    out = ctypes.create_string_buffer(size)
+    written = c_uint64(0)
+    check(lib().sonic_prove_shard(srs._h, ch.h, _frs(assignment.aL), _frs(assignment.aR), _frs(assignment.aO),
+                                  _frs(rnd), rank, world, out, size, ctypes.byref(written)))
+    return out.raw[:written.value]
+
+
+def prove_combine(Q: int, blobs: Sequence[bytes]) -> bytes:
+    """Folds the gathered shard blobs into the proof bytes (sonic_prove_combine)."""
+    capi.init()
+    size = int(lib().sonic_proof_size(Q))
+    out = ctypes.create_string_buffer(size)
+    written = c_uint64(0)
+    check(lib().sonic_prove_combine(Q, len(blobs), b"".join(blobs), out, size, ctypes.byref(written)))
+    return out.raw[:written.value]

@@ -47,15 +47,23 @@ SYMBOLS = {
     "sonic_msm_g1_partial": (c_int, [c_void_p, c_int, c_int64, c_uint64, _u8p, _u8p]),
     "sonic_g1_sum": (c_int, [_u8p, c_uint64, _u8p]),
     "sonic_msm_g1_device": (c_int, [c_void_p, c_int, c_int64, c_uint64, c_void_p, _u8p]),
+    "sonic_msm_g1_device_partial": (c_int, [c_void_p, c_int, c_int64, c_uint64, c_void_p, _u8p]),
     "sonic_circuit_load": (c_int, [c_uint64, c_uint64, _u8p, _u8p, _u8p, _u8p, POINTER(c_void_p)]),
     "sonic_circuit_free": (None, [c_void_p]),
     "sonic_rnd_count": (c_uint64, [c_uint64]),
     "sonic_proof_size": (c_uint64, [c_uint64]),
     "sonic_prove": (c_int, [c_void_p, c_void_p, _u8p, _u8p, _u8p, _u8p, _u8p, c_uint64, POINTER(c_uint64)]),
+    "sonic_shard_blob_size": (c_uint64, [c_uint64]),
+    "sonic_prove_shard": (c_int, [c_void_p, c_void_p, _u8p, _u8p, _u8p, _u8p, ctypes.c_uint32, ctypes.c_uint32, _u8p, c_uint64, POINTER(c_uint64)]),
+    "sonic_prove_combine": (c_int, [c_uint64, ctypes.c_uint32, _u8p, _u8p, c_uint64, POINTER(c_uint64)]),
+    "sonic_prove_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, _u8p, _u8p, c_uint64, POINTER(c_uint64)]),
+    "sonic_prove_shard_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, _u8p, ctypes.c_uint32, ctypes.c_uint32, _u8p, c_uint64, POINTER(c_uint64)]),
     "sonic_hsc_prove": (c_int, [c_void_p, c_void_p, c_uint64, _u8p, _u8p, _u8p, c_uint64, POINTER(c_uint64)]),
     "sonic_set_option": (c_int, [c_char_p, c_int64]),
     "sonic_last_timing_ms": (c_double, [c_char_p]),
     "sonic_launch_count": (c_uint64, []),
+    "sonic_bench_mark": (c_int, [c_int]),
+    "sonic_bench_elapsed_ms": (c_double, [c_int, c_int]),
     "sonic_imad_peak_lmacs": (c_double, [c_int, c_int]),
     "sonic_selftest_field": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, ctypes.c_uint32]),
     "sonic_selftest_g1": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_uint32]),

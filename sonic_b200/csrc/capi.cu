@@ -90,27 +90,36 @@ __global__ void k_sum_raw(const Fq* __restrict__ raw, uint32_t n, uint8_t* __res
 }
 
 // ---- IMAD microbenchmark: register-only chains of 32x32->64 multiply-accumulates ----------
+// Eight independent accumulator chains per thread; every product takes the chain's own low
+// word as one factor so that nothing can be hoisted or shared between chains.
+//   variant 0: mad.lo.cc / madc.hi.cc pairs (what the field multiplier issues; IMAD.WIDE.U32 + carry)
+//   variant 1: mad.wide.u32 on a 64-bit accumulator (IMAD.WIDE.U32, no carry)
+//   variant 2: separate mad.lo.u32 and mad.hi.u32 (two IMADs per product)
 template <int VARIANT>
 __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* out, uint32_t seed, int iters) {
-    uint32_t a = seed + threadIdx.x, b = seed * 3u + blockIdx.x;
-    uint32_t lo[8], hi[8];
+    uint32_t lo[8], hi[8], m[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { lo[k] = a + k; hi[k] = b + k; }
+    for (int k = 0; k < 8; ++k) { lo[k] = seed + threadIdx.x * 8 + k; hi[k] = seed * 3u + blockIdx.x + k; m[k] = (seed >> 3) + 2 * k + 1; }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int rep = 0; rep < 8; ++rep) {
-            if (VARIANT == 0) {
-                // independent carry-chained pairs, as in the field multiplier
 #pragma unroll
-                for (int k = 0; k < 8; ++k) Chain::mad_wide_cc(lo[k], hi[k], a, b, lo[k], hi[k]);
-            } else {
-                // plain mad.wide.u32 on 64-bit accumulators
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < 8; ++k) {
+                if (VARIANT == 0) {
+                    uint32_t nl, nh;
+                    asm volatile("mad.lo.cc.u32 %0, %2, %3, %4; madc.hi.u32 %1, %2, %3, %5;"
+                                 : "=&r"(nl), "=r"(nh) : "r"(lo[k]), "r"(m[k]), "r"(lo[k]), "r"(hi[k]));
+                    lo[k] = nl; hi[k] = nh;
+                } else if (VARIANT == 1) {
                     uint64_t acc = ((uint64_t)hi[k] << 32) | lo[k];
-                    asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a), "r"(b));
+                    asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(lo[k]), "r"(m[k]));
                     lo[k] = (uint32_t)acc;
                     hi[k] = (uint32_t)(acc >> 32);
+                } else {
+                    uint32_t nl, nh;
+                    asm volatile("mad.lo.u32 %0, %2, %3, %4; mad.hi.u32 %1, %2, %3, %5;"
+                                 : "=&r"(nl), "=r"(nh) : "r"(lo[k]), "r"(m[k]), "r"(lo[k]), "r"(hi[k]));
+                    lo[k] = nl; hi[k] = nh;
                 }
             }
         }
@@ -410,6 +419,11 @@ int sonic_msm_g1_device(const sonic_srs* srs, int family, int64_t lo, uint64_t l
     return msm_common(srs, family, lo, len, nullptr, d_scalars32, out, nullptr);
 }
 
+int sonic_msm_g1_device_partial(const sonic_srs* srs, int family, int64_t lo, uint64_t len, const void* d_scalars32, uint8_t out_raw[96]) {
+    if (!out_raw) return fail(SONIC_ERR_INVALID_ARG, "null output");
+    return msm_common(srs, family, lo, len, nullptr, d_scalars32, nullptr, out_raw);
+}
+
 int sonic_g1_sum(const uint8_t* raw96, uint64_t n, uint8_t out[48]) {
     if ((!raw96 && n) || !out || n > (1u << 20)) return fail(SONIC_ERR_INVALID_ARG, "bad argument");
     return guarded([&](Ctx& cx) {
@@ -537,7 +551,60 @@ int sonic_prove(const sonic_srs* srs, const sonic_circuit* circuit, const uint8_
         SONIC_CUDA(cudaMemcpyAsync(d_in + n, aR, n * 32, cudaMemcpyHostToDevice, cx.stream));
         SONIC_CUDA(cudaMemcpyAsync(d_in + 2 * n, aO, n * 32, cudaMemcpyHostToDevice, cx.stream));
         const Fr* d_rnd = upload_fr(cx, rnd, 2 * Q + 8);
-        int rc = prove_run(cx, srs, circuit, d_in, d_rnd, (uint32_t)Q, true, proof_out, cap, written);
+        int rc = prove_run(cx, srs, circuit, d_in, d_rnd, (uint32_t)Q, true, 0, 1, proof_out, cap, written);
+        tm.stop();
+        return rc;
+    });
+}
+
+uint64_t sonic_shard_blob_size(uint64_t Q) { return (4 * Q + 7) * 96 + (2 * Q + 5) * 32; }
+
+int sonic_prove_shard(const sonic_srs* srs, const sonic_circuit* circuit, const uint8_t* aL, const uint8_t* aR,
+                      const uint8_t* aO, const uint8_t* rnd, uint32_t rank, uint32_t world, uint8_t* blob_out,
+                      uint64_t cap, uint64_t* written) {
+    if (!srs || !circuit || !aL || !aR || !aO || !rnd || !blob_out) return fail(SONIC_ERR_INVALID_ARG, "null argument");
+    if (world < 2 || rank >= world || world > 64) return fail(SONIC_ERR_INVALID_ARG, "need 2 <= world <= 64 and rank < world");
+    const uint64_t n = circuit_n(circuit), Q = circuit_Q(circuit);
+    if (srs->d < 7 * n)
+        return fail(SONIC_ERR_D_TOO_SMALL, "Parameter d is not large enough: %" PRIu64 " should be greater than %" PRIu64, srs->d, 7 * n);
+    for (uint64_t i = 4; i < 2 * Q + 8; ++i)
+        if (fr_bytes_zero(rnd + 32 * i)) return fail(SONIC_ERR_DIV_BY_ZERO, "prove: recip 0 (challenge %" PRIu64 " is zero)", i);
+    return guarded([&](Ctx& cx) {
+        Timer tm(cx);
+        Fr* d_in = cx.arena.get<Fr>(3 * n);
+        SONIC_CUDA(cudaMemcpyAsync(d_in, aL, n * 32, cudaMemcpyHostToDevice, cx.stream));
+        SONIC_CUDA(cudaMemcpyAsync(d_in + n, aR, n * 32, cudaMemcpyHostToDevice, cx.stream));
+        SONIC_CUDA(cudaMemcpyAsync(d_in + 2 * n, aO, n * 32, cudaMemcpyHostToDevice, cx.stream));
+        const Fr* d_rnd = upload_fr(cx, rnd, 2 * Q + 8);
+        int rc = prove_run(cx, srs, circuit, d_in, d_rnd, (uint32_t)Q, true, rank, world, blob_out, cap, written);
+        tm.stop();
+        return rc;
+    });
+}
+
+int sonic_prove_combine(uint64_t Q, uint32_t world, const uint8_t* blobs, uint8_t* proof_out, uint64_t cap, uint64_t* written) {
+    if (!blobs || !proof_out || world < 1 || world > 64 || Q == 0 || Q >= (1u << 16)) return fail(SONIC_ERR_INVALID_ARG, "bad argument");
+    return guarded([&](Ctx& cx) { return prove_combine(cx, (uint32_t)Q, true, world, blobs, proof_out, cap, written); });
+}
+
+int sonic_prove_device(const sonic_srs* srs, const sonic_circuit* circuit, const void* d_assignment,
+                       const void* d_rnd, const uint8_t* rnd_host, uint8_t* proof_out, uint64_t cap, uint64_t* written) {
+    return sonic_prove_shard_device(srs, circuit, d_assignment, d_rnd, rnd_host, 0, 1, proof_out, cap, written);
+}
+
+int sonic_prove_shard_device(const sonic_srs* srs, const sonic_circuit* circuit, const void* d_assignment,
+                             const void* d_rnd, const uint8_t* rnd_host, uint32_t rank, uint32_t world,
+                             uint8_t* proof_out, uint64_t cap, uint64_t* written) {
+    if (!srs || !circuit || !d_assignment || !d_rnd || !rnd_host || !proof_out) return fail(SONIC_ERR_INVALID_ARG, "null argument");
+    if (world < 1 || rank >= world || world > 64) return fail(SONIC_ERR_INVALID_ARG, "need 1 <= world <= 64 and rank < world");
+    const uint64_t n = circuit_n(circuit), Q = circuit_Q(circuit);
+    if (srs->d < 7 * n)
+        return fail(SONIC_ERR_D_TOO_SMALL, "Parameter d is not large enough: %" PRIu64 " should be greater than %" PRIu64, srs->d, 7 * n);
+    for (uint64_t i = 4; i < 2 * Q + 8; ++i)
+        if (fr_bytes_zero(rnd_host + 32 * i)) return fail(SONIC_ERR_DIV_BY_ZERO, "prove: recip 0 (challenge %" PRIu64 " is zero)", i);
+    return guarded([&](Ctx& cx) {
+        Timer tm(cx);
+        int rc = prove_run(cx, srs, circuit, (const Fr*)d_assignment, (const Fr*)d_rnd, (uint32_t)Q, true, rank, world, proof_out, cap, written);
         tm.stop();
         return rc;
     });
@@ -559,7 +626,7 @@ int sonic_hsc_prove(const sonic_srs* srs, const sonic_circuit* circuit, uint64_t
     return guarded([&](Ctx& cx) {
         Timer tm(cx);
         const Fr* d_rnd = upload_fr(cx, rnd.data(), 2 * m + 8);
-        int rc = prove_run(cx, srs, circuit, nullptr, d_rnd, (uint32_t)m, false, out, cap, written);
+        int rc = prove_run(cx, srs, circuit, nullptr, d_rnd, (uint32_t)m, false, 0, 1, out, cap, written);
         tm.stop();
         return rc;
     });
@@ -590,6 +657,26 @@ double sonic_last_timing_ms(const char* stage) {
 
 uint64_t sonic_launch_count(void) { return ctx().launches; }
 
+int sonic_bench_mark(int slot) {
+    if (slot < 0 || slot > 5) return fail(SONIC_ERR_INVALID_ARG, "bench mark slot must be in [0, 5]");
+    Ctx& cx = ctx();
+    if (!cx.ready) return fail(SONIC_ERR_NOT_INITIALISED, "sonic_init has not been called");
+    std::lock_guard<std::mutex> lock(cx.mu);
+    if (cudaEventRecord(cx.ev[10 + slot], cx.stream) != cudaSuccess) return fail(SONIC_ERR_CUDA, "cudaEventRecord failed");
+    return SONIC_OK;
+}
+
+double sonic_bench_elapsed_ms(int from_slot, int to_slot) {
+    if (from_slot < 0 || from_slot > 5 || to_slot < 0 || to_slot > 5) return -1.0;
+    Ctx& cx = ctx();
+    if (!cx.ready) return -1.0;
+    std::lock_guard<std::mutex> lock(cx.mu);
+    float ms = -1.0f;
+    if (cudaEventSynchronize(cx.ev[10 + to_slot]) != cudaSuccess) return -1.0;
+    if (cudaEventElapsedTime(&ms, cx.ev[10 + from_slot], cx.ev[10 + to_slot]) != cudaSuccess) return -1.0;
+    return ms;
+}
+
 double sonic_imad_peak_lmacs(int variant, int iters) {
     double result = 0;
     int rc = guarded([&](Ctx& cx) {
@@ -599,7 +686,8 @@ double sonic_imad_peak_lmacs(int variant, int iters) {
         for (int rep = 0; rep < 3; ++rep) {
             SONIC_CUDA(cudaEventRecord(cx.ev[4], cx.stream));
             if (variant == 0) SONIC_LAUNCH(k_imad_peak<0>, blocks, threads, 0, out, 12345u, iters);
-            else SONIC_LAUNCH(k_imad_peak<1>, blocks, threads, 0, out, 12345u, iters);
+            else if (variant == 1) SONIC_LAUNCH(k_imad_peak<1>, blocks, threads, 0, out, 12345u, iters);
+            else SONIC_LAUNCH(k_imad_peak<2>, blocks, threads, 0, out, 12345u, iters);
             SONIC_CUDA(cudaEventRecord(cx.ev[5], cx.stream));
             SONIC_CUDA(cudaStreamSynchronize(cx.stream));
             float ms = 0;

@@ -93,7 +93,8 @@ struct Ctx {
     int opt_window_bits = 0;
     int opt_chunk = 0;
     std::map<std::string, double> timing_ms;
-    cudaEvent_t ev[8] = {};
+    const uint32_t* msm_offsets_total = nullptr;  // device address of the last batch's entry count
+    cudaEvent_t ev[16] = {};  // 0-3,8,9 msm stages; 4,5 poly / microbench; 6,7 call timer; 10-15 bench marks
     char* pinned = nullptr;  // staging for small D2H results
     size_t pinned_cap = 0;
 };

@@ -89,8 +89,12 @@ uint64_t circuit_n(const sonic_circuit* c);
 uint64_t circuit_Q(const sonic_circuit* c);
 // d_in: canonical aL|aR|aO (3n Fr); d_rnd: canonical draws in the reference's order, 2M+8 of them
 // (M = number of (y_j, z_j) pairs; M = Q inside `prove`).
+// world == 1: `out` receives the proof.  world > 1: this rank's slice of every MSM; `out` receives a
+// shard blob (raw partial sums + field values) for prove_combine.
 int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr* d_in, const Fr* d_rnd,
-              uint32_t M, bool has_main, uint8_t* out, uint64_t cap, uint64_t* written);
+              uint32_t M, bool has_main, uint32_t rank, uint32_t world, uint8_t* out, uint64_t cap, uint64_t* written);
+int prove_combine(Ctx& cx, uint32_t M, bool has_main, uint32_t world, const uint8_t* blobs, uint8_t* out,
+                  uint64_t cap, uint64_t* written);
 }  // namespace sonic
 
 // Resident SRS.  Device layout: one array of affine points indexed by exponent,

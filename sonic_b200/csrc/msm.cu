@@ -366,7 +366,16 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const uint32_t* d_scalars,
     G1XYZZ* buckets = ar.get<G1XYZZ>(p.GB);
     G1XYZZ* head = ar.get<G1XYZZ>(chunks ? chunks : 1);
     G1XYZZ* tail = ar.get<G1XYZZ>(chunks ? chunks : 1);
+    SONIC_CUDA(cudaEventRecord(cx.ev[8], st));
     if (chunks) SONIC_LAUNCH(k_msm_accumulate, div_up(chunks, 128), 128, 0, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
+    SONIC_CUDA(cudaEventRecord(cx.ev[9], st));
+    cx.timing_ms["msm.window_bits"] = p.c;
+    cx.timing_ms["msm.windows"] = p.W;
+    cx.timing_ms["msm.terms"] = n_tot;
+    cx.timing_ms["msm.jobs"] = M;
+    cx.timing_ms["msm.chunk"] = p.L;
+    cx.timing_ms["msm.buckets"] = p.GB;
+    cx.msm_offsets_total = offsets + p.GB;
     uint32_t* heavy_count = ar.get<uint32_t>(1);
     uint32_t* heavy_list = ar.get<uint32_t>((size_t)chunks / MSM_HEAVY_PIECES + 2);
     SONIC_CUDA(cudaMemsetAsync(heavy_count, 0, 4, st));
@@ -389,6 +398,12 @@ void msm_collect_timing(Ctx& cx) {
         cx.timing_ms["msm.accumulate"] = b;
         cx.timing_ms["msm.reduce"] = c;
         cx.timing_ms["msm"] = a + b + c;
+    }
+    float k = 0;
+    if (cudaEventElapsedTime(&k, cx.ev[8], cx.ev[9]) == cudaSuccess) cx.timing_ms["msm.accumulate_kernel"] = k;
+    if (cx.msm_offsets_total) {
+        uint32_t total = 0;
+        if (cudaMemcpy(&total, cx.msm_offsets_total, 4, cudaMemcpyDeviceToHost) == cudaSuccess) cx.timing_ms["msm.entries"] = total;
     }
 }
 

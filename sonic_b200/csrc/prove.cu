@@ -230,15 +230,73 @@ struct ProofMsm {
 // d_rnd: canonical draws.  has_main = false computes only the hscProve part, with
 // d_rnd holding ys[Q] zs[Q] u v at the positions they have in the full draw order.
 // Outputs (host): proof bytes in record order.
+// Proof bytes from the G1 encodings (record order, 48 B each) and the Fr values (record order).
+static void assemble_proof(bool has_main, uint32_t M, const uint8_t* g48, const uint8_t* f32, uint8_t* out) {
+    uint8_t* o = out;
+    auto putG = [&]() { memcpy(o, g48, 48); o += 48; g48 += 48; };
+    auto putF = [&]() { memcpy(o, f32, 32); o += 32; f32 += 32; };
+    if (has_main) { putG(); putG(); putF(); putG(); putF(); putG(); putG(); putF(); }  // prR prT prA prWa prB prWb prWt prS
+    for (uint32_t j = 0; j < M; ++j) { putG(); putF(); putG(); }                        // (S_j, (s_j, W_j))
+    for (uint32_t j = 0; j < M; ++j) { putF(); putG(); putG(); }                        // (s'_j, W'_j, Q_j)
+    putG(); putG(); putF(); putF();                                                     // hscQv hscC hscU hscV
+}
+
+// affine Montgomery -> raw 96 bytes (canonical little-endian x || y; infinity = zeros)
+__global__ void k_points_to_raw(const G1Affine* __restrict__ pts, uint32_t n, Fq* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[2 * i] = fp_from_mont(pts[i].x);
+    out[2 * i + 1] = fp_from_mont(pts[i].y);
+}
+
+// out48[m] = compress(sum_r raw[r][m]),  raw laid out [world][nm] x 96 B
+__global__ void k_fold_partials(const Fq* __restrict__ raw, uint32_t nm, uint32_t world, uint8_t* __restrict__ out48) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nm) return;
+    G1XYZZ acc = G1XYZZ::inf();
+    for (uint32_t r = 0; r < world; ++r) {
+        const Fq* p = raw + 2 * ((size_t)r * nm + m);
+        G1Affine a;
+        a.x = fp_to_mont(p[0]);
+        a.y = fp_to_mont(p[1]);
+        g1_madd(acc, a);  // (0,0) marks infinity and is skipped
+    }
+    g1_compress(g1_to_affine(acc), out48 + (size_t)m * 48);
+}
+
+// Sharded proofs: every rank runs the Fr side in full and the slice [rank/world, (rank+1)/world)
+// of every MSM; its output is then a "shard blob" = nm raw partial sums (96 B) followed by the
+// nF field values (32 B) in record order.  prove_combine folds the gathered blobs.
+int prove_combine(Ctx& cx, uint32_t M, bool has_main, uint32_t world, const uint8_t* blobs, uint8_t* out,
+                  uint64_t cap, uint64_t* written) {
+    const uint32_t nm = has_main ? 4 * M + 7 : 4 * M + 2;
+    const uint32_t nF = has_main ? 2 * M + 5 : 2 * M + 2;
+    const uint64_t blob = (uint64_t)nm * 96 + (uint64_t)nF * 32;
+    const uint64_t need = (uint64_t)nm * 48 + (uint64_t)nF * 32;
+    if (written) *written = need;
+    if (cap < need) return fail(SONIC_ERR_BUFFER_TOO_SMALL, "proof needs %llu bytes", (unsigned long long)need);
+    Fq* d_raw = cx.arena.get<Fq>(2 * (size_t)nm * world);
+    for (uint32_t r = 0; r < world; ++r)
+        SONIC_CUDA(cudaMemcpyAsync(d_raw + 2 * (size_t)r * nm, blobs + r * blob, (size_t)nm * 96, cudaMemcpyHostToDevice, cx.stream));
+    uint8_t* d_out = cx.arena.get<uint8_t>((size_t)nm * 48);
+    SONIC_LAUNCH(k_fold_partials, div_up(nm, 32), 32, 0, d_raw, nm, world, d_out);
+    std::vector<uint8_t> g48((size_t)nm * 48);
+    SONIC_CUDA(cudaMemcpyAsync(g48.data(), d_out, g48.size(), cudaMemcpyDeviceToHost, cx.stream));
+    SONIC_CUDA(cudaStreamSynchronize(cx.stream));
+    assemble_proof(has_main, M, g48.data(), blobs + (size_t)nm * 96, out);
+    return SONIC_OK;
+}
+
 int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr* d_in, const Fr* d_rnd,
-              uint32_t M, bool has_main, uint8_t* out, uint64_t cap, uint64_t* written) {
+              uint32_t M, bool has_main, uint32_t rank, uint32_t world, uint8_t* out, uint64_t cap, uint64_t* written) {
     const uint32_t n = (uint32_t)circ->n, Q = (uint32_t)circ->Q;
     const int64_t d = (int64_t)srs->d;
     const uint32_t nG = has_main ? 4 * M + 7 : 4 * M + 2;
     const uint32_t nF = has_main ? 2 * M + 5 : 2 * M + 2;
-    const uint64_t need = (uint64_t)nG * 48 + (uint64_t)nF * 32;
+    const bool sharded = world > 1;
+    const uint64_t need = (uint64_t)nG * (sharded ? 96 : 48) + (uint64_t)nF * 32;
     if (written) *written = need;
-    if (cap < need) return fail(SONIC_ERR_BUFFER_TOO_SMALL, "proof needs %llu bytes", (unsigned long long)need);
+    if (cap < need) return fail(SONIC_ERR_BUFFER_TOO_SMALL, "output needs %llu bytes", (unsigned long long)need);
     Arena& ar = cx.arena;
     cudaStream_t st = cx.stream;
     SONIC_CUDA(cudaEventRecord(cx.ev[4], st));
@@ -398,6 +456,7 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
     uint32_t* viol = ar.get<uint32_t>(3 * (size_t)nm);
     SONIC_CUDA(cudaMemsetAsync(viol, 0xff, 12 * (size_t)nm, st));
     std::vector<MsmJob> jobs(nm);
+    std::vector<int64_t> slice_lo(nm, 0);
     struct Rng { int64_t a, b; };
     std::vector<Rng> rngs(3 * (size_t)nm, Rng{0, 0});
     for (uint32_t i = 0; i < nm; ++i) {
@@ -413,7 +472,14 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
                 SONIC_LAUNCH(k_first_nonzero_job, div_up(b - a, 256), 256, 0, m.scal, a, b, viol + 3 * (size_t)i + k);
             }
         }
-        const int64_t clo = std::max(lo, -d), chi = std::max(clo, std::min(hi, d + 1));
+        int64_t clo = std::max(lo, -d), chi = std::max(clo, std::min(hi, d + 1));
+        if (sharded) {  // this rank's contiguous slice of the exponent window
+            const int64_t span = chi - clo;
+            const int64_t a = clo + span * (int64_t)rank / (int64_t)world, b = clo + span * (int64_t)(rank + 1) / (int64_t)world;
+            clo = a;
+            chi = b;
+        }
+        slice_lo[i] = clo;
         jobs[i].point_base = (uint32_t)srs->index(m.family, clo);
         jobs[i].n = (uint32_t)(chi - clo);
         // scalar_off is relative to one base pointer: use the arena base of the first job
@@ -423,10 +489,8 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
     // all scalar vectors live in the arena; express them as offsets from the lowest address
     const Fr* sbase = pm[0].scal;
     for (const ProofMsm& m : pm) if (m.scal < sbase) sbase = m.scal;
-    for (uint32_t i = 0; i < nm; ++i) {
-        const int64_t clo = std::max(pm[i].lo, -d);
-        jobs[i].scalar_off = (uint32_t)((pm[i].scal - sbase) + (clo - pm[i].lo));
-    }
+    for (uint32_t i = 0; i < nm; ++i)
+        jobs[i].scalar_off = (uint32_t)((pm[i].scal - sbase) + (slice_lo[i] - pm[i].lo));
     G1Affine* d_aff = ar.get<G1Affine>(nm);
     uint8_t* d_comp = ar.get<uint8_t>((size_t)nm * 48);
     for (uint32_t first = 0; first < nm; first += MSM_MAX_JOBS) {
@@ -436,12 +500,18 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
     }
 
     // ---- results to the host ---------------------------------------------------------------------
-    std::vector<uint8_t> h_comp((size_t)nm * 48);
+    std::vector<uint8_t> h_comp((size_t)nm * (sharded ? 96 : 48));
     std::vector<Fr> h_vals(nvals ? nvals : 1);
     std::vector<uint32_t> h_viol(3 * (size_t)nm);
     std::vector<Fr> h_rnd(nr);
     uint32_t h_bad = 0;
-    SONIC_CUDA(cudaMemcpyAsync(h_comp.data(), d_comp, h_comp.size(), cudaMemcpyDeviceToHost, st));
+    if (sharded) {
+        Fq* d_raw = ar.get<Fq>(2 * (size_t)nm);
+        SONIC_LAUNCH(k_points_to_raw, div_up(nm, 64), 64, 0, d_aff, nm, d_raw);
+        SONIC_CUDA(cudaMemcpyAsync(h_comp.data(), d_raw, h_comp.size(), cudaMemcpyDeviceToHost, st));
+    } else {
+        SONIC_CUDA(cudaMemcpyAsync(h_comp.data(), d_comp, h_comp.size(), cudaMemcpyDeviceToHost, st));
+    }
     SONIC_CUDA(cudaMemcpyAsync(h_vals.data(), vals, nvals * sizeof(Fr), cudaMemcpyDeviceToHost, st));
     SONIC_CUDA(cudaMemcpyAsync(h_viol.data(), viol, h_viol.size() * 4, cudaMemcpyDeviceToHost, st));
     SONIC_CUDA(cudaMemcpyAsync(h_rnd.data(), d_rnd, nr * sizeof(Fr), cudaMemcpyDeviceToHost, st));
@@ -467,27 +537,23 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
             return fail(SONIC_ERR_SRS_TOO_SHORT, "openPoly: gNegativeX is not long enough: %lld >= %llu", (long long)(-e - 1), (unsigned long long)dd);
         }
 
-    // ---- proof bytes in record order (Protocol.hs:28-38, Signature.hs:22-29) ---------------------
-    uint8_t* o = out;
-    uint32_t g = 0;
-    auto putG = [&]() { memcpy(o, h_comp.data() + (size_t)g * 48, 48); o += 48; ++g; };
-    auto putF = [&](const Fr& v) { memcpy(o, v.l, 32); o += 32; };
-    if (has_main) {
-        putG();               // prR
-        putG();               // prT
-        putF(h_vals[v_a]);    // prA
-        putG();               // prWa
-        putF(h_vals[v_b]);    // prB
-        putG();               // prWb
-        putG();               // prWt
-        putF(h_vals[v_s]);    // prS
+    // ---- field values in record order (Protocol.hs:28-38, Signature.hs:22-29) ---------------------
+    std::vector<uint8_t> f32((size_t)nF * 32);
+    {
+        uint8_t* o = f32.data();
+        auto putF = [&](const Fr& v) { memcpy(o, v.l, 32); o += 32; };
+        if (has_main) { putF(h_vals[v_a]); putF(h_vals[v_b]); putF(h_vals[v_s]); }   // prA prB prS
+        for (uint32_t j = 0; j < M; ++j) putF(h_vals[v_sj[j]]);                       // s_j
+        for (uint32_t j = 0; j < M; ++j) putF(h_vals[v_spj[j]]);                      // s'_j
+        putF(h_rnd[6 + 2 * M]);                                                       // hscU
+        putF(h_rnd[7 + 2 * M]);                                                       // hscV
     }
-    for (uint32_t j = 0; j < M; ++j) { putG(); putF(h_vals[v_sj[j]]); putG(); }     // (S_j, (s_j, W_j))
-    for (uint32_t j = 0; j < M; ++j) { putF(h_vals[v_spj[j]]); putG(); putG(); }    // (s'_j, W'_j, Q_j)
-    putG();                        // hscQv
-    putG();                        // hscC
-    putF(h_rnd[6 + 2 * M]);        // hscU
-    putF(h_rnd[7 + 2 * M]);        // hscV
+    if (sharded) {
+        memcpy(out, h_comp.data(), h_comp.size());
+        memcpy(out + h_comp.size(), f32.data(), f32.size());
+    } else {
+        assemble_proof(has_main, M, h_comp.data(), f32.data(), out);
+    }
     (void)v_t; (void)v_qv; (void)v_wpj;
     return SONIC_OK;
 }

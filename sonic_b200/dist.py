@@ -1,0 +1,47 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed for the exchange.
+
+The path shards two ways: across independent proofs (no exchange at all)
+and, for one proof, across contiguous slices of every MSM.  The second has exactly one
+exchange step: each rank ends with 4Q+7 partial G1 sums (96 B each) plus the field values;
+one all-gather of that small blob (NCCL over NVLink on GPUs, gloo in the CPU tests) and a
+fold with `<>` complete the proof.  Nothing else crosses ranks: the SRS is replicated.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def slice_bounds(lo: int, hi: int, rank: int, world: int) -> Tuple[int, int]:
+    """The contiguous part [a, b) of an exponent window [lo, hi) that `rank` of `world` sums
+    (same arithmetic as prove_run in csrc/prove.cu)."""
+    span = hi - lo
+    return lo + span * rank // world, lo + span * (rank + 1) // world
+
+
+def all_gather_bytes(blob: bytes, group=None) -> List[bytes]:
+    """All-gather of one fixed-size byte blob per rank; returns the blobs in rank order."""
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(device)
+    out = torch.empty(world * mine.numel(), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    flat = out.cpu().numpy().tobytes()
+    n = len(blob)
+    return [flat[i * n:(i + 1) * n] for i in range(world)]
+
+
+def prove_sharded(srs, assignment, circuit, rnd: Sequence[int], group=None) -> bytes:
+    """One proof over all ranks of `group`; every rank returns the same proof bytes."""
+    from . import api
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world == 1:
+        return api.prove_bytes(srs, assignment, circuit, rnd)
+    blob = api.prove_shard(srs, assignment, circuit, rnd, rank, world)
+    blobs = all_gather_bytes(blob, group)
+    return api.prove_combine(circuit.handle().Q, blobs)

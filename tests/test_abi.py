@@ -1,0 +1,92 @@
+"""CPU: the C-ABI library loads and exports every symbol include/sonic_b200.h declares; the
+host-side logic (argument checks, error text) behaves without a GPU; there is no CPU fallback."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sonic_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sonic_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from sonic_b200 import capi
+
+    names = _declared_symbols()
+    assert len(names) >= 25
+    L = ctypes.CDLL(capi.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), f"{n} is declared in include/sonic_b200.h but not exported"
+    # the Python binding covers the whole header too
+    assert set(names) == set(capi.SYMBOLS), set(names) ^ set(capi.SYMBOLS)
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a usable GPU every compute entry point fails loudly instead of computing on the CPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the no-device path is exercised on the CPU box")
+    from sonic_b200 import capi
+
+    L = capi.lib()
+    dev = (ctypes.c_int * 1)(0)
+    rc = L.sonic_init(dev, 1)
+    assert rc == 8, rc  # SONIC_ERR_NO_DEVICE
+    assert "no CPU fallback" in capi.last_error()
+    h = ctypes.c_void_p()
+    one = (1).to_bytes(32, "little")
+    assert L.sonic_srs_new(4, one, one, ctypes.byref(h)) == 9  # NOT_INITIALISED
+    out = ctypes.create_string_buffer(48)
+    assert L.sonic_g1_sum(None, 0, out) == 9
+    import sonic_b200
+
+    with pytest.raises(sonic_b200.SonicError) as e:
+        sonic_b200.SRS.new(4, 3, 5)
+    assert e.value.kind == "NO_DEVICE"
+
+
+def test_host_side_argument_checks():
+    from sonic_b200 import capi
+
+    L = capi.lib()
+    h = ctypes.c_void_p()
+    one = (1).to_bytes(32, "little")
+    zero = bytes(32)
+    r = (0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001).to_bytes(32, "little")
+    assert L.sonic_srs_new(4, zero, one, ctypes.byref(h)) == 4       # recip 0
+    assert "recip 0" in capi.last_error()
+    assert L.sonic_srs_new(4, r, one, ctypes.byref(h)) == 5          # x = r is not canonical
+    assert L.sonic_srs_new(0, one, one, ctypes.byref(h)) == 1
+    assert L.sonic_rnd_count(8) == 24
+    assert L.sonic_proof_size(8) == 39 * 48 + 21 * 32
+    assert L.sonic_strerror(3) == b"parameter d is not large enough"
+    assert L.sonic_set_option(b"window_bits", 99) == 1
+    assert L.sonic_set_option(b"window_bits", 0) == 0
+
+
+def test_synthetic_generators_are_deterministic_and_canonical():
+    from sonic_b200 import synth
+
+    a = synth.fr_bytes_fast(7, 1000)
+    b = synth.fr_bytes_fast(7, 1000)
+    assert (a == b).all() and a.shape == (1000, 32)
+    R = synth.R_MODULUS
+    for row in a[:50]:
+        assert int.from_bytes(bytes(row), "little") < R
+    sk = synth.skewed_fr_bytes(3, 4000)
+    vals = [int.from_bytes(bytes(r), "little") for r in sk]
+    assert 0.4 < sum(v == 0 for v in vals) / 4000 < 0.6
+    assert 0.15 < sum(v in (1, R - 1) for v in vals) / 4000 < 0.35
+    (wL, wR, wO, cs), (aL, aR, aO) = synth.synthetic_circuit(6, 3, 2)
+    for q in range(3):
+        dot = lambda v, row: sum(x * y for x, y in zip(v, row))
+        assert (dot(aL, wL[q]) + dot(aR, wR[q]) + dot(aO, wO[q])) % R == cs[q]
+    c = synth.synthetic_circuit_bytes(6, 3, 2)
+    assert c["ints"]["cs"] == cs and bytes(c["aL"]) == synth.ints_to_bytes(aL)

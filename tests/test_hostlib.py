@@ -1,0 +1,108 @@
+"""CPU: the device arithmetic headers compiled for the host (portable emulation of the PTX
+carry chain) against Python big ints: the exact limb algorithms of field.cuh / g1.cuh /
+scalar.cuh, without a GPU."""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+
+from oracle import bls12_381 as bls
+from tests.util import from_limbs, limbs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+Q, R = bls.Q, bls.R
+
+
+@pytest.fixture(scope="module")
+def host():
+    src = os.path.join(ROOT, "tests", "hostlib", "hostlib.cpp")
+    so = os.path.join(ROOT, "tests", "hostlib", "libsonic_hosttest.so")
+    deps = [src] + [os.path.join(ROOT, "sonic_b200", "csrc", f) for f in ("field.cuh", "g1.cuh", "scalar.cuh", "constants.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
+    return ctypes.CDLL(so)
+
+
+def _arr(v, n):
+    return (ctypes.c_uint32 * n)(*limbs(v, n))
+
+
+@pytest.mark.parametrize("field", ["fq", "fr"])
+def test_montgomery_field_ops(host, field):
+    fn, n, p = (host.ht_fq_op, 12, Q) if field == "fq" else (host.ht_fr_op, 8, R)
+    Rm = 1 << (32 * n)
+    Ri = pow(Rm, -1, p)
+    rng = random.Random(31)
+
+    def op(k, a, b=0):
+        out = (ctypes.c_uint32 * n)()
+        fn(k, _arr(a, n), _arr(b, n), out)
+        return from_limbs(out)
+
+    edge = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, Rm % p]
+    samples = [(a, b) for a in edge for b in edge] + [(rng.randrange(p), rng.randrange(p)) for _ in range(1500)]
+    for a, b in samples:
+        assert op(0, a, b) == a * b * Ri % p
+        assert op(1, a, b) == (a + b) % p
+        assert op(2, a, b) == (a - b) % p
+        assert op(3, a) == a * Rm % p
+        assert op(4, a) == a * Ri % p
+        assert op(6, a) == a * a * Ri % p
+        assert op(7, a) == (-a) % p
+    for _ in range(10):
+        a = rng.randrange(1, p)
+        assert op(5, a * Rm % p) == pow(a, -1, p) * Rm % p
+
+
+def test_g1_formulas_all_cases(host):
+    Rm = 1 << 384
+    rng = random.Random(32)
+
+    def aff(P):
+        return _arr(0 if P is None else (P[0] * Rm % Q) | ((P[1] * Rm % Q) << 384), 24)
+
+    def xyzz(P, z):
+        if P is None:
+            return _arr((Rm % Q) | ((Rm % Q) << 384), 48)
+        zz, zzz = z * z % Q, z * z * z % Q
+        return _arr((P[0] * zz % Q * Rm % Q) | ((P[1] * zzz % Q * Rm % Q) << 384) | ((zz * Rm % Q) << 768) | ((zzz * Rm % Q) << 1152), 48)
+
+    def to_aff(x):
+        out = (ctypes.c_uint32 * 24)()
+        host.ht_g1_to_affine(x, out)
+        v = from_limbs(out)
+        xm, ym = v & ((1 << 384) - 1), v >> 384
+        if xm == 0 and ym == 0:
+            return None
+        Ri = pow(Rm, -1, Q)
+        return (xm * Ri % Q, ym * Ri % Q)
+
+    G = bls.G1_GEN
+    pts = [None, G, bls.g1_neg(G)] + [bls.g1_mul_gen(rng.randrange(R)) for _ in range(5)]
+    for A in pts:
+        for B in pts:
+            out = (ctypes.c_uint32 * 48)()
+            host.ht_g1_op(0, xyzz(A, rng.randrange(2, Q)), aff(B), out)
+            assert to_aff(out) == bls.g1_add(A, B)
+            host.ht_g1_op(1, xyzz(A, rng.randrange(2, Q)), xyzz(B, rng.randrange(2, Q)), out)
+            assert to_aff(out) == bls.g1_add(A, B)
+        out = (ctypes.c_uint32 * 48)()
+        host.ht_g1_op(2, xyzz(A, rng.randrange(2, Q)), None, out)
+        assert to_aff(out) == bls.g1_add(A, A)
+        c = (ctypes.c_uint8 * 48)()
+        host.ht_g1_compress(aff(A), c)
+        assert bytes(c) == bls.g1_compress(A)
+
+
+def test_signed_digit_recoding(host):
+    rng = random.Random(33)
+    for c in range(4, 21):
+        W = (255 + c - 1) // c
+        cases = [0, 1, R - 1, (R - 1) // 2, (R - 1) // 2 + 1, 1 << (c - 1), (1 << (c - 1)) + 1] + [rng.randrange(R) for _ in range(100)]
+        for s in cases:
+            d = (ctypes.c_int32 * 80)()
+            assert host.ht_recode(_arr(s, 8), c, d) == W
+            assert sum(int(d[j]) << (c * j) for j in range(W)) % R == s
+            assert all(abs(int(d[j])) <= 1 << (c - 1) for j in range(W))
