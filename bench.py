@@ -300,7 +300,7 @@ def main() -> None:
     exec_lmac = stage["msm.entries"] * LMAC_PER_MADD
     achieved = canon_lmac / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else 0.0
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_accumulate_traffic.json")
+    tpath = sorted([os.path.join(ROOT, "profiles", f) for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_accumulate_traffic.json")] or [""])[-1]
     if os.path.exists(tpath):
         try:
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")

@@ -159,7 +159,10 @@ int sonic_hsc_prove(const sonic_srs* srs, const sonic_circuit* circuit, uint64_t
                     uint64_t* written);
 
 /* ---- tuning and measurement hooks (not part of the reference surface) ---- */
-/* option names: "window_bits" (0 = automatic), "chunk" (0 = automatic) */
+/* option names: "window_bits" (0 = automatic), "chunk" (0 = automatic),
+ * "precompute" (-1 = automatic, 0 = off, c = window bits): SRS.new also stores the multiples
+ * 2^(c j) * base of every SRS element so that all windows of an MSM share one bucket set;
+ * "precompute_budget_mb": HBM the automatic mode may spend on those tables (default 8192) */
 int sonic_set_option(const char* name, int64_t value);
 /* device time in milliseconds of the kernels of the last call, by stage name; returns 0
  * if unknown.  Stages: "msm", "msm.sort", "msm.accumulate", "msm.reduce", "msm.accumulate_kernel", "poly", "total";

@@ -210,7 +210,7 @@ int msm_window(Ctx& cx, const sonic_srs* srs, int family, bool commit_text, cons
     jobs[0].pad = 0;
     G1Affine* d_aff = cx.arena.get<G1Affine>(1);
     uint8_t* d_comp = cx.arena.get<uint8_t>(48);
-    msm_run(cx, srs->points, (const uint32_t*)d_scal, jobs, d_aff, d_comp);
+    msm_run(cx, srs->points, srs->tables, (const uint32_t*)d_scal, jobs, d_aff, d_comp);
     uint8_t* h = pinned(cx, 256);
     if (out48) SONIC_CUDA(cudaMemcpyAsync(h, d_comp, 48, cudaMemcpyDeviceToHost, cx.stream));
     if (out_raw96) {
@@ -333,7 +333,23 @@ int sonic_srs_new(uint64_t d, const uint8_t x[32], const uint8_t alpha[32], soni
         sonic_srs* s = new sonic_srs;
         s->d = d;
         const uint64_t npts = 2 * s->stride();
-        cudaError_t e = cudaMalloc((void**)&s->points, npts * sizeof(G1Affine));
+        // precomputed window multiples: automatic while they fit the memory budget
+        int pre_c = cx.opt_precompute;
+        if (pre_c < 0) {
+            int lg = 0;
+            while ((2ull << lg) <= d) ++lg;          // floor(log2 d)
+            pre_c = lg - 2;
+            if (pre_c < 4) pre_c = 4;
+            if (pre_c > 16) pre_c = 16;
+            const uint64_t W = (255 + pre_c - 1) / pre_c;
+            if (npts * W * sizeof(G1Affine) > cx.opt_precompute_budget) pre_c = 0;
+        }
+        uint64_t levels = pre_c > 0 ? (255 + pre_c - 1) / pre_c : 1;
+        if (npts * levels >= (1ull << 31)) { pre_c = 0; levels = 1; }
+        s->tables.c = pre_c;
+        s->tables.W = pre_c > 0 ? (int)levels : 0;
+        s->tables.stride = (uint32_t)npts;
+        cudaError_t e = cudaMalloc((void**)&s->points, npts * levels * sizeof(G1Affine));
         if (e != cudaSuccess) { delete s; throw CudaError{e, "cudaMalloc(srs)", __LINE__}; }
         try {
             Timer tm(cx);
@@ -342,7 +358,7 @@ int sonic_srs_new(uint64_t d, const uint8_t x[32], const uint8_t alpha[32], soni
             memcpy(h + 32, alpha, 32);
             Fr* d_canon = cx.arena.get<Fr>(2);
             SONIC_CUDA(cudaMemcpyAsync(d_canon, h, 64, cudaMemcpyHostToDevice, cx.stream));
-            srs_generate(cx, d, d_canon, s->points);
+            srs_generate(cx, d, d_canon, s->points, pre_c);
             tm.stop();
         } catch (...) {
             cudaFree(s->points);
@@ -639,6 +655,12 @@ int sonic_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "window_bits")) {
         if (value != 0 && (value < 4 || value > 20)) return fail(SONIC_ERR_INVALID_ARG, "window_bits must be 0 or in [4, 20]");
         cx.opt_window_bits = (int)value;
+    } else if (!strcmp(name, "precompute")) {
+        if (value != -1 && value != 0 && (value < 4 || value > 20)) return fail(SONIC_ERR_INVALID_ARG, "precompute must be -1 (auto), 0 (off) or window bits in [4, 20]");
+        cx.opt_precompute = (int)value;
+    } else if (!strcmp(name, "precompute_budget_mb")) {
+        if (value < 0) return fail(SONIC_ERR_INVALID_ARG, "budget must be >= 0");
+        cx.opt_precompute_budget = (uint64_t)value << 20;
     } else if (!strcmp(name, "chunk")) {
         if (value < 0 || value > 4096) return fail(SONIC_ERR_INVALID_ARG, "chunk must be in [0, 4096]");
         cx.opt_chunk = (int)value;

@@ -46,25 +46,45 @@ struct CudaError {
 
 // ---- context -----------------------------------------------------------------------------
 struct Arena {
-    // grow-only bump allocator: one cudaMalloc per high-water mark, reset per call
+    // Grow-only bump allocator over one device block, reset at the start of every call.  When a
+    // call outgrows the block, extra blocks are chained for the rest of that call and the next
+    // reset replaces everything with a single block sized for the high-water mark, so that a
+    // steady workload performs no cudaMalloc / cudaFree at all.
     char* base = nullptr;
     size_t cap = 0, off = 0;
+    size_t used = 0;             // bytes handed out during the current call (all blocks)
     std::vector<void*> retired;  // blocks outgrown during the current call (freed on reset)
 
     void reset() {
-        off = 0;
         for (void* p : retired) cudaFree(p);
+        const bool spilled = !retired.empty();
         retired.clear();
+        if (spilled || used > cap) {
+            if (base) cudaFree(base);
+            base = nullptr;
+            cap = 0;
+            size_t want = used + used / 4 + (size_t(16) << 20);
+            if (cudaMalloc((void**)&base, want) == cudaSuccess) cap = want;
+            else { base = nullptr; cudaGetLastError(); }
+        }
+        off = 0;
+        used = 0;
     }
     void* alloc(size_t bytes) {
         bytes = (bytes + 255) & ~size_t(255);
+        used += bytes;
         if (off + bytes > cap) {
-            // allocate a fresh, larger block; earlier pointers of this call stay valid
-            size_t ncap = cap ? cap : (size_t(64) << 20);
-            while (ncap < bytes) ncap <<= 1;
-            ncap = ncap < bytes * 2 ? bytes * 2 : ncap;
+            size_t ncap = cap * 2 > (size_t(64) << 20) ? cap * 2 : (size_t(64) << 20);
+            if (ncap < bytes * 2) ncap = bytes * 2;
             if (base) retired.push_back(base);
-            SONIC_CUDA(cudaMalloc((void**)&base, ncap));
+            base = nullptr;
+            cap = 0;
+            cudaError_t e = cudaMalloc((void**)&base, ncap);
+            if (e != cudaSuccess) {  // retry with exactly what is needed
+                cudaGetLastError();
+                ncap = bytes;
+                SONIC_CUDA(cudaMalloc((void**)&base, ncap));
+            }
             cap = ncap;
             off = 0;
         }
@@ -75,10 +95,11 @@ struct Arena {
     template <class T>
     T* get(size_t count) { return (T*)alloc(count * sizeof(T)); }
     void release() {
-        reset();
+        for (void* p : retired) cudaFree(p);
+        retired.clear();
         if (base) cudaFree(base);
         base = nullptr;
-        cap = 0;
+        cap = off = used = 0;
     }
 };
 
@@ -92,6 +113,8 @@ struct Ctx {
     uint64_t launches = 0;
     int opt_window_bits = 0;
     int opt_chunk = 0;
+    int opt_precompute = -1;                              // -1 auto, 0 off, else window bits
+    uint64_t opt_precompute_budget = uint64_t(8) << 30;   // bytes of HBM the auto mode may spend on tables
     std::map<std::string, double> timing_ms;
     const uint32_t* msm_offsets_total = nullptr;  // device address of the last batch's entry count
     cudaEvent_t ev[16] = {};  // 0-3,8,9 msm stages; 4,5 poly / microbench; 6,7 call timer; 10-15 bench marks

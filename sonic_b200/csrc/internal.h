@@ -28,15 +28,24 @@ struct MsmJobTable {
 
 // d_scalars: canonical little-endian scalars, 8 words each.  Results: one affine point
 // (Montgomery form) and/or one 48-byte compressed encoding per job, in device memory.
-void msm_run(Ctx& cx, const G1Affine* d_points, const uint32_t* d_scalars, const std::vector<MsmJob>& jobs,
-             G1Affine* d_out_aff, uint8_t* d_out_comp);
+// Precomputed window multiples of the bases: level j of the point array holds 2^(c j) * P for
+// every base P, `stride` points per level.  With them all windows of a job share one bucket set
+// (no per-window reduction, no Horner tail).  c == 0: no tables, plain windowed Pippenger.
+struct MsmTables {
+    int c = 0;
+    int W = 0;
+    uint32_t stride = 0;
+};
+void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const uint32_t* d_scalars,
+             const std::vector<MsmJob>& jobs, G1Affine* d_out_aff, uint8_t* d_out_comp);
 void msm_collect_timing(Ctx& cx);
 void exclusive_scan_u32(Arena& ar, const uint32_t* in, uint32_t* out, uint32_t n);
 
 
 // ---- srs.cu ------------------------------------------------------------------------------
 // Generates the resident point array.  d_canon: x, alpha canonical (2 Fr) in device memory.
-void srs_generate(Ctx& cx, uint64_t d, const Fr* d_canon, G1Affine* d_points);
+// pre_c > 0 additionally fills levels 1..W-1 with the 2^(pre_c j) multiples (W = ceil(255/pre_c)).
+void srs_generate(Ctx& cx, uint64_t d, const Fr* d_canon, G1Affine* d_points, int pre_c);
 
 // ---- poly.cu -----------------------------------------------------------------------------
 struct OpenJob {
@@ -102,7 +111,8 @@ int prove_combine(Ctx& cx, uint32_t M, bool has_main, uint32_t world, const uint
 // the alpha slot k = 0 holds the infinity marker (0,0) and is never referenced by a job.
 struct sonic_srs {
     uint64_t d = 0;
-    sonic::G1Affine* points = nullptr;  // 2*(2d+1) affine points, Montgomery form
+    sonic::G1Affine* points = nullptr;  // levels x 2*(2d+1) affine points, Montgomery form; level 0 is the SRS
+    sonic::MsmTables tables;            // precomputed window multiples (c == 0: level 0 only)
     uint64_t stride() const { return 2 * d + 1; }
     uint64_t index(int family, int64_t k) const { return (uint64_t)family * stride() + (uint64_t)(k + (int64_t)d); }
 };

@@ -34,6 +34,7 @@ namespace sonic {
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__ scalars, MsmJobTable tab,
                                                     uint32_t n_tot, int c, int W, uint32_t B,
+                                                    uint32_t level_stride,  // 0: one bucket set per window
                                                     uint32_t* __restrict__ counters,
                                                     uint32_t* __restrict__ entries) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -46,9 +47,12 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__
     uint32_t s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
     if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) return;
     ScalarDigits sd(s, c);
-    const uint32_t pid = tab.job[j].point_base + local;
-    uint32_t gb0 = (uint32_t)j * (uint32_t)W * B;
-    for (int w = 0; w < W; ++w, gb0 += B) {
+    uint32_t pid = tab.job[j].point_base + local;
+    // with precomputed multiples every window of a job feeds the same bucket set and the window
+    // index selects the table level instead
+    uint32_t gb0 = level_stride ? (uint32_t)j * B : (uint32_t)j * (uint32_t)W * B;
+    const uint32_t gb_step = level_stride ? 0u : B;
+    for (int w = 0; w < W; ++w, gb0 += gb_step, pid += level_stride) {
         int32_t d = sd.next();
         if (d == 0) continue;
         uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
@@ -285,11 +289,11 @@ k_msm_finish(const G1XYZZ* __restrict__ partial, uint32_t S, int W, int c, G1Aff
 
 // ---- host side ---------------------------------------------------------------------------
 struct MsmPlan {
-    int c, W;
+    int c, W, sets;
     uint32_t B, GB, L, K, S, n_tot;
 };
 
-static MsmPlan msm_plan(const Ctx& cx, uint32_t n_tot, int M) {
+static MsmPlan msm_plan(const Ctx& cx, uint32_t n_tot, int M, const MsmTables& tables) {
     MsmPlan p;
     int best_c = 8;
     double best = 1e300;
@@ -306,9 +310,11 @@ static MsmPlan msm_plan(const Ctx& cx, uint32_t n_tot, int M) {
     p.c = cx.opt_window_bits > 0 ? cx.opt_window_bits : best_c;
     if (p.c < 4) p.c = 4;
     if (p.c > 20) p.c = 20;
+    if (tables.c > 0) p.c = tables.c;  // the table levels fix the window
     p.W = msm_num_windows(p.c);
     p.B = 1u << (p.c - 1);
-    p.GB = (uint32_t)M * p.W * p.B;
+    p.sets = tables.c > 0 ? 1 : p.W;   // bucket sets per job
+    p.GB = (uint32_t)M * p.sets * p.B;
     p.n_tot = n_tot;
     // chunk length: enough chunks to fill the machine a few times over, capped for low fix-up cost
     uint64_t entries = (uint64_t)n_tot * p.W;
@@ -317,17 +323,24 @@ static MsmPlan msm_plan(const Ctx& cx, uint32_t n_tot, int M) {
     if (L < 8) L = 8;
     if (L > 64) L = 64;
     p.L = cx.opt_chunk > 0 ? (uint32_t)cx.opt_chunk : (uint32_t)L;
-    p.K = p.B / MSM_RED_THREADS;
+    // buckets per thread in the reduction: each thread pays ~25 extra point operations (its
+    // offset multiple and the block tree) on top of 2 per bucket, so K is as large as the
+    // machine fill allows
+    uint64_t all_buckets = (uint64_t)p.GB;
+    uint64_t kfill = all_buckets / ((uint64_t)cx.sm_count * 256 * 2);
+    p.K = (uint32_t)kfill;
+    if (p.K < 8) p.K = 8;
+    if (p.K > 64) p.K = 64;
+    if (p.K > p.B / MSM_RED_THREADS) p.K = p.B / MSM_RED_THREADS;
     if (p.K < 1) p.K = 1;
-    if (p.K > 8) p.K = 8;
     p.S = div_up(p.B, (uint64_t)MSM_RED_THREADS * p.K);
     return p;
 }
 
 // d_scalars: canonical little-endian scalars, 8 words each.  Results: one affine point
 // (Montgomery form) and/or one 48-byte compressed encoding per job, in device memory.
-void msm_run(Ctx& cx, const G1Affine* d_points, const uint32_t* d_scalars,
-                    const std::vector<MsmJob>& jobs, G1Affine* d_out_aff, uint8_t* d_out_comp) {
+void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const uint32_t* d_scalars,
+             const std::vector<MsmJob>& jobs, G1Affine* d_out_aff, uint8_t* d_out_comp) {
     const int M = (int)jobs.size();
     if (M == 0) return;
     if (M > MSM_MAX_JOBS) throw CudaError{cudaErrorInvalidValue, "too many MSM jobs", __LINE__};
@@ -344,7 +357,8 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const uint32_t* d_scalars,
     if (n_tot64 >= (1ull << 31)) throw CudaError{cudaErrorInvalidValue, "MSM batch too large", __LINE__};
     const uint32_t n_tot = (uint32_t)n_tot64;
     Arena& ar = cx.arena;
-    MsmPlan p = msm_plan(cx, n_tot, M);
+    MsmPlan p = msm_plan(cx, n_tot, M, tables);
+    const uint32_t level_stride = tables.c > 0 ? tables.stride : 0u;
     if ((uint64_t)n_tot * p.W >= (1ull << 32)) throw CudaError{cudaErrorInvalidValue, "MSM batch too large", __LINE__};
     cudaStream_t st = cx.stream;
 
@@ -352,14 +366,14 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const uint32_t* d_scalars,
     uint32_t* offsets = ar.get<uint32_t>((size_t)p.GB + 1);
     uint32_t* cursors = ar.get<uint32_t>((size_t)p.GB + 1);
     SONIC_CUDA(cudaMemsetAsync(offsets, 0, ((size_t)p.GB + 1) * 4, st));
-    if (n_tot) SONIC_LAUNCH(k_msm_digits<false>, div_up(n_tot, 256), 256, 0, d_scalars, tab, n_tot, p.c, p.W, p.B, offsets, (uint32_t*)nullptr);
+    if (n_tot) SONIC_LAUNCH(k_msm_digits<false>, div_up(n_tot, 256), 256, 0, d_scalars, tab, n_tot, p.c, p.W, p.B, level_stride, offsets, (uint32_t*)nullptr);
     exclusive_scan_u32(ar, offsets, offsets, p.GB + 1);
     SONIC_CUDA(cudaMemcpyAsync(cursors, offsets, ((size_t)p.GB + 1) * 4, cudaMemcpyDeviceToDevice, st));
     // zero digits are not stored, so n_tot*W is only an upper bound of the entry count; the
     // accumulate grid is sized for the bound and reads the true count from offsets[GB]
     const uint64_t total_max = (uint64_t)n_tot * p.W;
     uint32_t* entries = ar.get<uint32_t>(total_max ? total_max : 1);
-    if (n_tot) SONIC_LAUNCH(k_msm_digits<true>, div_up(n_tot, 256), 256, 0, d_scalars, tab, n_tot, p.c, p.W, p.B, cursors, entries);
+    if (n_tot) SONIC_LAUNCH(k_msm_digits<true>, div_up(n_tot, 256), 256, 0, d_scalars, tab, n_tot, p.c, p.W, p.B, level_stride, cursors, entries);
     SONIC_CUDA(cudaEventRecord(cx.ev[1], st));
 
     const uint32_t chunks = div_up(total_max, p.L);
@@ -371,6 +385,7 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const uint32_t* d_scalars,
     SONIC_CUDA(cudaEventRecord(cx.ev[9], st));
     cx.timing_ms["msm.window_bits"] = p.c;
     cx.timing_ms["msm.windows"] = p.W;
+    cx.timing_ms["msm.precomputed"] = tables.c > 0 ? 1 : 0;
     cx.timing_ms["msm.terms"] = n_tot;
     cx.timing_ms["msm.jobs"] = M;
     cx.timing_ms["msm.chunk"] = p.L;
@@ -383,9 +398,9 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const uint32_t* d_scalars,
     SONIC_LAUNCH(k_msm_heavy, cx.sm_count * 2, MSM_RED_THREADS, 0, offsets, p.L, buckets, head, tail, heavy_count, heavy_list);
     SONIC_CUDA(cudaEventRecord(cx.ev[2], st));
 
-    G1XYZZ* partial = ar.get<G1XYZZ>((size_t)M * p.W * p.S);
-    SONIC_LAUNCH(k_msm_bucket_reduce, dim3(p.S, (unsigned)(M * p.W)), MSM_RED_THREADS, 0, buckets, p.B, p.K, partial);
-    SONIC_LAUNCH(k_msm_finish, M, 64, 0, partial, p.S, p.W, p.c, d_out_aff, d_out_comp);
+    G1XYZZ* partial = ar.get<G1XYZZ>((size_t)M * p.sets * p.S);
+    SONIC_LAUNCH(k_msm_bucket_reduce, dim3(p.S, (unsigned)(M * p.sets)), MSM_RED_THREADS, 0, buckets, p.B, p.K, partial);
+    SONIC_LAUNCH(k_msm_finish, M, 64, 0, partial, p.S, p.sets, p.c, d_out_aff, d_out_comp);
     SONIC_CUDA(cudaEventRecord(cx.ev[3], st));
 }
 

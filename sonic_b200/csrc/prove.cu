@@ -496,7 +496,7 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
     for (uint32_t first = 0; first < nm; first += MSM_MAX_JOBS) {
         const uint32_t cnt = std::min<uint32_t>(MSM_MAX_JOBS, nm - first);
         std::vector<MsmJob> part(jobs.begin() + first, jobs.begin() + first + cnt);
-        msm_run(cx, srs->points, (const uint32_t*)sbase, part, d_aff + first, d_comp + (size_t)first * 48);
+        msm_run(cx, srs->points, srs->tables, (const uint32_t*)sbase, part, d_aff + first, d_comp + (size_t)first * 48);
     }
 
     // ---- results to the host ---------------------------------------------------------------------

@@ -32,7 +32,7 @@ __global__ void k_srs_params(const Fr* __restrict__ canon, Fr* __restrict__ mont
     }
 }
 
-// scal[0][k+d] = x^k, scal[1][k+d] = alpha x^k, canonical form, k in [-d, d]
+// scal[0][k+d] = x^k, scal[1][k+d] = alpha x^k, Montgomery form, k in [-d, d]
 __global__ void __launch_bounds__(128) k_srs_scalars(const Fr* __restrict__ mont, uint64_t d, Fr* __restrict__ scal) {
     const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const bool negative = blockIdx.y == 1;
@@ -46,10 +46,25 @@ __global__ void __launch_bounds__(128) k_srs_scalars(const Fr* __restrict__ mont
         const uint64_t e = e0 + i;
         if (e > d) break;
         const uint64_t idx = negative ? d - e : d + e;
-        scal[idx] = fp_from_mont(v);
-        scal[stride + idx] = fp_from_mont(fp_mul(v, alpha));
+        scal[idx] = v;
+        scal[stride + idx] = fp_mul(v, alpha);
         v = fp_mul(v, base);
     }
+}
+
+// consts[j] = 2^(c j) (Montgomery), j < W
+__global__ void k_level_consts(int c, int W, Fr* __restrict__ consts) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= W) return;
+    Fr v = Fr::one();
+    for (int i = 0; i < c * j; ++i) v = fp_dbl(v);
+    consts[j] = v;
+}
+
+// out[i] = canonical(scal[i] * factor)
+__global__ void __launch_bounds__(256) k_level_scalars(const Fr* __restrict__ scal, const Fr* __restrict__ factor, uint64_t n, Fr* __restrict__ out) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = fp_from_mont(fp_mul(scal[i], *factor));
 }
 
 // T[j][0] = inf, T[j][1] = 2^(w j) G
@@ -142,14 +157,19 @@ static int srs_table_bits(uint64_t npoints) {
 }
 
 // Generates the resident point array.  d_canon: x, alpha canonical (2 Fr) in device memory.
-void srs_generate(Ctx& cx, uint64_t d, const Fr* d_canon, G1Affine* d_points) {
+// Level 0 is the SRS itself; with pre_c > 0, level j holds the same points times 2^(pre_c j),
+// obtained from the same fixed-base table with the scalar multiplied by 2^(pre_c j) mod r.
+void srs_generate(Ctx& cx, uint64_t d, const Fr* d_canon, G1Affine* d_points, int pre_c) {
     Arena& ar = cx.arena;
     const uint64_t stride = 2 * d + 1, npts = 2 * stride;
+    const int levels = pre_c > 0 ? (255 + pre_c - 1) / pre_c : 1;
     Fr* mont = ar.get<Fr>(3);
     SONIC_LAUNCH(k_srs_params, 1, 32, 0, d_canon, mont);
-    Fr* scal = ar.get<Fr>(npts);
-    SONIC_LAUNCH(k_srs_scalars, dim3(div_up(d / SRS_RUN + 1, 128), 2), 128, 0, mont, d, scal);
-    const int w = srs_table_bits(npts);
+    Fr* scal_m = ar.get<Fr>(npts);
+    SONIC_LAUNCH(k_srs_scalars, dim3(div_up(d / SRS_RUN + 1, 128), 2), 128, 0, mont, d, scal_m);
+    Fr* consts = ar.get<Fr>(levels);
+    SONIC_LAUNCH(k_level_consts, div_up(levels, 32), 32, 0, pre_c > 0 ? pre_c : 1, levels, consts);
+    const int w = srs_table_bits(npts * (uint64_t)levels);
     const int Wt = (255 + w - 1) / w;
     const size_t tsize = (size_t)Wt << w;
     G1XYZZ* Tx = ar.get<G1XYZZ>(tsize);
@@ -158,11 +178,14 @@ void srs_generate(Ctx& cx, uint64_t d, const Fr* d_canon, G1Affine* d_points) {
     for (int l = 1; l < w; ++l)
         SONIC_LAUNCH(k_tbl_level, dim3(div_up(1u << l, 128), (unsigned)Wt), 128, 0, Tx, w, Wt, l);
     SONIC_LAUNCH(k_batch_affine, div_up(div_up(tsize, AFF_BATCH), 128), 128, 0, Tx, Ta, (uint64_t)tsize);
+    Fr* scal = ar.get<Fr>(npts);
     G1XYZZ* px = ar.get<G1XYZZ>(npts);
     const uint64_t hole = stride + d;  // alpha family, exponent 0: g^alpha is not part of the SRS
-    SONIC_LAUNCH(k_fixed_base, div_up(npts, 128), 128, 0, scal, Ta, w, Wt, npts, hole, px);
-    SONIC_LAUNCH(k_batch_affine, div_up(div_up(npts, AFF_BATCH), 128), 128, 0, px, d_points, npts);
+    for (int j = 0; j < levels; ++j) {
+        SONIC_LAUNCH(k_level_scalars, div_up(npts, 256), 256, 0, scal_m, consts + j, npts, scal);
+        SONIC_LAUNCH(k_fixed_base, div_up(npts, 128), 128, 0, scal, Ta, w, Wt, npts, hole, px);
+        SONIC_LAUNCH(k_batch_affine, div_up(div_up(npts, AFF_BATCH), 128), 128, 0, px, d_points + (size_t)j * npts, npts);
+    }
 }
-
 
 }  // namespace sonic
