@@ -777,3 +777,24 @@ def assemble_proof_bytes(Q: int, g48: Sequence[bytes], fvals: Sequence[int]) -> 
         fi += 1
     out += [g[gi], g[gi + 1], f[fi], f[fi + 1]]
     return b"".join(out)
+
+
+def verify_trapdoor_dense(srs_d: int, x: int, alpha: int, circuit: ArithCircuit, proof: Proof, y: int, z: int, yzs) -> bool:
+    """`verify` (/root/reference/src/Sonic/Protocol.hs:111-130 with Signature.hs:74-90) through
+    dense vectors and the trapdoor form of `pcV`; needs no SRS vectors, so it scales to n = 2^16."""
+    n = len(circuit.weights.wL[0])
+    w = circuit.weights
+    srs = SRS(srsD=srs_d, gNegativeX=[], gPositiveX=[], gNegativeAlphaX=[], gPositiveAlphaX=[], x=x % R, alpha=alpha % R)
+    ky = sum(k * fr_pow(y, n + 1 + q) for q, k in enumerate(circuit.cs)) % R
+    t = (proof.prA * (proof.prB + proof.prS) - ky) % R
+    h = proof.prHscProof
+    ok = pcV_trapdoor(srs, n, proof.prR, z, (proof.prA, proof.prWa))
+    ok = ok and pcV_trapdoor(srs, n, proof.prR, y * z % R, (proof.prB, proof.prWb))
+    ok = ok and pcV_trapdoor(srs, srs_d, proof.prT, z, (t, proof.prWt))
+    sv = dense_sXy(w, h.hscV).eval(h.hscU)
+    ok = ok and pcV_trapdoor(srs, srs_d, h.hscC, h.hscV, (sv, h.hscQv))
+    for (yi, zi), (ci, (si, wi)), (sip, wip, qi) in zip(yzs, h.hscS, h.hscW):
+        ok = ok and pcV_trapdoor(srs, srs_d, ci, zi, (si, wi))
+        ok = ok and pcV_trapdoor(srs, srs_d, ci, h.hscU, (sip, wip))
+        ok = ok and pcV_trapdoor(srs, srs_d, h.hscC, yi, (sip, qi))
+    return bool(ok)

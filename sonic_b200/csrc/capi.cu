@@ -661,6 +661,9 @@ int sonic_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "precompute_budget_mb")) {
         if (value < 0) return fail(SONIC_ERR_INVALID_ARG, "budget must be >= 0");
         cx.opt_precompute_budget = (uint64_t)value << 20;
+    } else if (!strcmp(name, "acc_blocks")) {
+        if (value < 2 || value > 5) return fail(SONIC_ERR_INVALID_ARG, "acc_blocks must be in [2, 5]");
+        cx.opt_acc_blocks = (int)value;
     } else if (!strcmp(name, "chunk")) {
         if (value < 0 || value > 4096) return fail(SONIC_ERR_INVALID_ARG, "chunk must be in [0, 4096]");
         cx.opt_chunk = (int)value;

@@ -213,8 +213,9 @@ SONIC_HD void mont_row_next(uint32_t* pe, uint32_t* po, const uint32_t* a, uint3
     mont_reduce_row<P>(po, pe);
 }
 
+// Fully unrolled variant: 2N^2+N IMADs in one straight line (about 420 SASS instructions for Fq).
 template <class P>
-SONIC_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+SONIC_HD Fp<P> fp_mul_unrolled(const Fp<P>& a, const Fp<P>& b) {
     constexpr int N = P::N;
     static_assert(N % 2 == 0, "even limb count");
     uint32_t ev[N], od[N];
@@ -232,6 +233,46 @@ SONIC_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
     r.l[N - 1] = Chain::addc(ev[N - 1], 0);
     fp_reduce_once(r);
     return r;
+}
+
+// Rolled variant: the same rows, two per loop iteration (so the accumulator roles return to
+// where they started), the multiplier limbs rotated through registers.  Same IMAD count, one
+// sixth of the code: a point addition then fits the instruction cache, which the fully
+// unrolled form (67 KB per mixed addition) does not.
+template <class P>
+SONIC_HD Fp<P> fp_mul_rolled(const Fp<P>& a, const Fp<P>& b) {
+    constexpr int N = P::N;
+    static_assert(N % 2 == 0, "even limb count");
+    uint32_t ev[N], od[N], bb[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) { ev[k] = 0; od[k] = 0; bb[k] = b.l[k]; }
+#pragma unroll 1
+    for (int i = 0; i < N; i += 2) {
+        mont_row_next<P>(ev, od, a.l, bb[0]);  // even-aligned now in od
+        mont_row_next<P>(od, ev, a.l, bb[1]);  // and back in ev
+#pragma unroll
+        for (int k = 0; k < N - 2; ++k) bb[k] = bb[k + 2];
+    }
+    Fp<P> r;
+    r.l[0] = Chain::add_cc(ev[1], od[0]);
+#pragma unroll
+    for (int k = 1; k < N - 1; ++k) r.l[k] = Chain::addc_cc(ev[k + 1], od[k]);
+    r.l[N - 1] = Chain::addc(od[N - 1], 0);
+    fp_reduce_once(r);
+    return r;
+}
+
+#ifndef SONIC_MUL_ROLLED
+#define SONIC_MUL_ROLLED 0
+#endif
+
+template <class P>
+SONIC_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+#if SONIC_MUL_ROLLED
+    return fp_mul_rolled(a, b);
+#else
+    return fp_mul_unrolled(a, b);
+#endif
 }
 
 template <class P>

@@ -140,7 +140,8 @@ SONIC_D G1Affine fetch_entry(const G1Affine* __restrict__ points, uint32_t e) {
     return p;
 }
 
-__global__ void __launch_bounds__(128, 3)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_msm_accumulate(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets, uint32_t GB,
                  uint32_t L, const G1Affine* __restrict__ points,
                  G1XYZZ* __restrict__ buckets, G1XYZZ* __restrict__ head, G1XYZZ* __restrict__ tail) {
@@ -381,7 +382,13 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const u
     G1XYZZ* head = ar.get<G1XYZZ>(chunks ? chunks : 1);
     G1XYZZ* tail = ar.get<G1XYZZ>(chunks ? chunks : 1);
     SONIC_CUDA(cudaEventRecord(cx.ev[8], st));
-    if (chunks) SONIC_LAUNCH(k_msm_accumulate, div_up(chunks, 128), 128, 0, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
+    if (chunks) {
+        if (cx.opt_acc_blocks == 5) SONIC_LAUNCH(k_msm_accumulate<5>, div_up(chunks, 128), 128, 0, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
+        else if (cx.opt_acc_blocks == 4) SONIC_LAUNCH(k_msm_accumulate<4>, div_up(chunks, 128), 128, 0, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
+        else if (cx.opt_acc_blocks == 2) SONIC_LAUNCH(k_msm_accumulate<2>, div_up(chunks, 128), 128, 0, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
+        else if (cx.opt_acc_blocks == 3) SONIC_LAUNCH(k_msm_accumulate<3>, div_up(chunks, 128), 128, 0, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
+        else SONIC_LAUNCH(k_msm_accumulate<2>, div_up(chunks, 128), 128, 0, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
+    }
     SONIC_CUDA(cudaEventRecord(cx.ev[9], st));
     cx.timing_ms["msm.window_bits"] = p.c;
     cx.timing_ms["msm.windows"] = p.W;

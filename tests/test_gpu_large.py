@@ -1,0 +1,144 @@
+"""GPU, BASELINE.json sizes: properties that do not need an O(N) CPU recomputation of the group
+work -- trapdoor identities (one Fr evaluation + one scalar multiplication checks an MSM of any
+size), verify(prove) == True, idempotence across option settings -- plus config 2 (n = 2^12)
+byte-for-byte against the C restatement of the reference algorithm."""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+from oracle import bls12_381 as bls
+from oracle import cref
+from oracle import sonic as S
+from sonic_b200 import synth
+
+pytestmark = pytest.mark.gpu
+R = bls.R
+C = bls.g1_compress
+
+
+def _horner_window(scal_bytes: np.ndarray, x: int, lo: int) -> int:
+    """sum_k s_k x^(lo+k) mod r."""
+    acc = 0
+    data = scal_bytes.tobytes()
+    for k in range(len(scal_bytes) - 1, -1, -1):
+        acc = (acc * x + int.from_bytes(data[32 * k:32 * k + 32], "little")) % R
+    return acc * S.fr_pow(x, lo) % R
+
+
+@pytest.fixture(scope="module")
+def big_srs(gpu):
+    x, alpha = synth.trapdoor()
+    return gpu.SRS.new(1 << 19, x, alpha), x, alpha
+
+
+@pytest.mark.parametrize("kind", ["uniform", "skewed"])
+def test_msm_2pow20_trapdoor_identity(gpu, big_srs, kind):
+    """Config 3 at N = 2^20: sum_k s_k g^{x^k} == g^{sum_k s_k x^k}; plain and alpha families."""
+    srs, x, alpha = big_srs
+    N = 1 << 20
+    sc = synth.fr_bytes_fast(20, N) if kind == "uniform" else synth.skewed_fr_bytes(20, N)
+    lo = -(N // 2)
+    e = _horner_window(sc, x, lo)
+    assert gpu.msm(srs, 0, lo, sc) == C(bls.g1_mul_gen(e))
+    sc2 = sc.copy()
+    sc2[N // 2] = 0  # alpha family: nothing may sit on g^alpha
+    e2 = _horner_window(sc2, x, lo) * alpha % R
+    assert gpu.msm(srs, 1, lo, sc2) == C(bls.g1_mul_gen(e2))
+
+
+def test_msm_result_independent_of_tuning_options(gpu, big_srs):
+    """Window size, chunk length and the precomputed tables are performance knobs: the group
+    element must not move (idempotence across algorithms)."""
+    x, alpha = synth.trapdoor()
+    N = 1 << 17
+    sc = synth.skewed_fr_bytes(3, N)
+    results = set()
+    try:
+        for pre in (-1, 0):
+            gpu.set_option("precompute", pre)
+            srs = gpu.SRS.new(1 << 16, x, alpha)
+            for wb, chunk in ((0, 0), (9, 8), (15, 64), (18, 16)):
+                gpu.set_option("window_bits", wb)
+                gpu.set_option("chunk", chunk)
+                results.add(gpu.msm(srs, 0, -(N // 2), sc))
+            srs.free()
+    finally:
+        gpu.set_option("precompute", -1)
+        gpu.set_option("window_bits", 0)
+        gpu.set_option("chunk", 0)
+    assert len(results) == 1
+    assert results.pop() == C(bls.g1_mul_gen(_horner_window(sc, x, -(N // 2))))
+
+
+def _prove_bytes(gpu, srs, c, rnd_ints):
+    from sonic_b200 import capi
+    L = capi.lib()
+    ch = ctypes.c_void_p()
+    capi.check(L.sonic_circuit_load(c["n"], c["Q"], c["wL"].ctypes.data, c["wR"].ctypes.data, c["wO"].ctypes.data,
+                                    c["cs"].ctypes.data, ctypes.byref(ch)))
+    rnd = np.frombuffer(synth.ints_to_bytes(rnd_ints), dtype=np.uint8).copy()
+    out = ctypes.create_string_buffer(int(L.sonic_proof_size(c["Q"])))
+    w = ctypes.c_uint64(0)
+    capi.check(L.sonic_prove(srs._h, ch, c["aL"].ctypes.data, c["aR"].ctypes.data, c["aO"].ctypes.data, rnd.ctypes.data,
+                             out, len(out), ctypes.byref(w)))
+    L.sonic_circuit_free(ch)
+    return out.raw
+
+
+def test_config2_prove_n4096_matches_reference_algorithm(gpu):
+    """BASELINE config 2: synthetic circuit n = 2^12, Q = 8, d = 7n (3n+9 makes the reference's
+    prove panic); the CUDA proof equals the C restatement's byte for byte, and the
+    commitR MSM alone is also checked at d = 3n+9."""
+    n, Q = 1 << 12, 8
+    d = 7 * n
+    x, alpha = synth.trapdoor()
+    c = synth.synthetic_circuit_bytes(n, Q, seed=2)
+    rnd = [v or 1 for v in synth.fr_ints(22, 2 * Q + 8)]
+    srs = gpu.SRS.new(d, x, alpha)
+    got = _prove_bytes(gpu, srs, c, rnd)
+    table = cref.srs_new(d, x, alpha, threads=16)
+    want = cref.prove(table, d, n, Q, c["wL"], c["wR"], c["wO"], c["cs"], c["aL"], c["aR"], c["aO"],
+                      np.frombuffer(synth.ints_to_bytes(rnd), dtype=np.uint8).copy(), threads=16)
+    assert got == want
+    # commitR at d = 3n+9: r'(X,1) shifted by d - n stays inside the SRS
+    d2 = 3 * n + 9
+    srs2 = gpu.SRS.new(d2, x, alpha)
+    ints = c["ints"]
+    rx1 = S.dense_rX1(S.Assignment(ints["aL"], ints["aR"], ints["aO"]), rnd[0:4])
+    fx = rx1.eval(x)
+    assert gpu.commitPoly(srs2, n, rx1.to_sparse()) == C(bls.g1_mul_gen(alpha * S.fr_pow(x, d2 - n) * fx))
+    with pytest.raises(gpu.SonicError) as e:
+        _prove_bytes(gpu, srs2, c, rnd)
+    assert e.value.text == f"Parameter d is not large enough: {d2} should be greater than {7 * n}"
+
+
+def test_config4_prove_n65536_verifies(gpu):
+    """BASELINE config 4: n = 2^16, Q = 8, d = 7n.  verify(prove(...)) == True (pcV in the exponent
+    with the trapdoor), two proofs with the same draws are identical, and R, T satisfy the
+    commitment identities."""
+    n, Q = 1 << 16, 8
+    d = 7 * n
+    x, alpha = synth.trapdoor()
+    c = synth.synthetic_circuit_bytes(n, Q, seed=4)
+    rnd = [v or 1 for v in synth.fr_ints(40, 2 * Q + 8)]
+    srs = gpu.SRS.new(d, x, alpha)
+    got = _prove_bytes(gpu, srs, c, rnd)
+    assert got == _prove_bytes(gpu, srs, c, rnd)
+    proof = S.decode_proof(got, Q)
+    ints = c["ints"]
+    one_row = lambda row: [[1] * n if q == row else [0] * n for q in range(Q)]
+    rows = ints["rows"]
+    circuit = S.ArithCircuit(S.GateWeights(one_row(rows[0]), one_row(rows[1]), one_row(rows[2])), ints["cs"])
+    y, z = rnd[4], rnd[5]
+    yzs = list(zip(rnd[6:6 + Q], rnd[6 + Q:6 + 2 * Q]))
+    assert S.verify_trapdoor_dense(d, x, alpha, circuit, proof, y, z, yzs)
+    rx1 = S.dense_rX1(S.Assignment(ints["aL"], ints["aR"], ints["aO"]), rnd[0:4])
+    assert proof.prR == bls.g1_mul_gen(alpha * S.fr_pow(x, d - n) * rx1.eval(x))
+    assert proof.prA == rx1.eval(z) and proof.prB == rx1.eval(y * z % R)
+    # a different blinder changes R but still verifies
+    rnd2 = list(rnd)
+    rnd2[0] = (rnd2[0] + 1) % R
+    p2 = S.decode_proof(_prove_bytes(gpu, srs, c, rnd2), Q)
+    assert p2.prR != proof.prR and S.verify_trapdoor_dense(d, x, alpha, circuit, p2, y, z, yzs)
