@@ -288,6 +288,8 @@ void sonic_shutdown(void) {
     cudaSetDevice(cx.device);
     cudaStreamSynchronize(cx.stream);
     cx.arena.release();
+    for (auto& kv : cx.ntt_cache) cudaFree(kv.second);
+    cx.ntt_cache.clear();
     if (cx.pinned) cudaFreeHost(cx.pinned);
     cx.pinned = nullptr;
     cx.pinned_cap = 0;

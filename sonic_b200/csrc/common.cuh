@@ -113,10 +113,11 @@ struct Ctx {
     uint64_t launches = 0;
     int opt_window_bits = 0;
     int opt_chunk = 0;
-    int opt_acc_blocks = 2;                               // resident blocks/SM the accumulate kernel is compiled for (2, 3, 4)
+    int opt_acc_blocks = 3;                               // resident blocks/SM the accumulate kernel is compiled for (2, 3, 4)
     int opt_precompute = -1;                              // -1 auto, 0 off, else window bits
     uint64_t opt_precompute_budget = uint64_t(8) << 30;   // bytes of HBM the auto mode may spend on tables
     std::map<std::string, double> timing_ms;
+    std::map<uint32_t, void*> ntt_cache;  // log2(length) -> resident twiddle tables
     const uint32_t* msm_offsets_total = nullptr;  // device address of the last batch's entry count
     cudaEvent_t ev[16] = {};  // 0-3,8,9 msm stages; 4,5 poly / microbench; 6,7 call timer; 10-15 bench marks
     char* pinned = nullptr;  // staging for small D2H results

@@ -262,21 +262,263 @@ SONIC_HD Fp<P> fp_mul_rolled(const Fp<P>& a, const Fp<P>& b) {
     return r;
 }
 
-#ifndef SONIC_MUL_ROLLED
-#define SONIC_MUL_ROLLED 0
+// ---- wide (unreduced) products and a separate Montgomery reduction -----------------------
+// Splitting "multiply" from "reduce" lets the multiplier spend fewer IMADs than the interleaved
+// CIOS above: (1) one level of Karatsuba on the 2K x 2K limb product (3 K x K products instead
+// of 4: 108 instead of 144 IMADs for Fq), paid for with additions that run on the ALU pipe, which
+// idles while the IMAD pipe is saturated; (2) sums of two products are reduced once (fp_mul_add2).
+
+// K x K schoolbook product with the same even/odd accumulator trick (K even): out[2K] = a * b.
+template <int K>
+SONIC_HD void wide_mul(uint32_t* out, const uint32_t* a, const uint32_t* b) {
+    static_assert(K % 2 == 0, "even limb count");
+    uint32_t E[2 * K + 2], O[2 * K + 2];  // O[k] holds limb k+1
+#pragma unroll
+    for (int k = 0; k < 2 * K + 2; ++k) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+    for (int j = 0; j < K; j += 2) {
+        Chain::mul_wide(E[j], E[j + 1], a[j], b[0]);
+        Chain::mul_wide(O[j], O[j + 1], a[j + 1], b[0]);
+    }
+#pragma unroll
+    for (int i = 1; i < K; ++i) {
+        if (i & 1) {
+            // odd row: a[even j] lands on odd positions i+j -> O[i+j-1]; a[odd j] on even positions -> E[i+j]
+            Chain::mad_wide_cc(O[i - 1], O[i], a[0], b[i], O[i - 1], O[i]);
+#pragma unroll
+            for (int j = 2; j < K; j += 2) Chain::madc_wide_cc(O[i + j - 1], O[i + j], a[j], b[i], O[i + j - 1], O[i + j]);
+            O[i + K - 1] = Chain::addc(O[i + K - 1], 0);
+            Chain::mad_wide_cc(E[i + 1], E[i + 2], a[1], b[i], E[i + 1], E[i + 2]);
+#pragma unroll
+            for (int j = 3; j < K; j += 2) Chain::madc_wide_cc(E[i + j], E[i + j + 1], a[j], b[i], E[i + j], E[i + j + 1]);
+            E[i + K + 1] = Chain::addc(E[i + K + 1], 0);
+        } else {
+            // even row: a[even j] on even positions -> E[i+j]; a[odd j] on odd positions -> O[i+j-1]
+            Chain::mad_wide_cc(E[i], E[i + 1], a[0], b[i], E[i], E[i + 1]);
+#pragma unroll
+            for (int j = 2; j < K; j += 2) Chain::madc_wide_cc(E[i + j], E[i + j + 1], a[j], b[i], E[i + j], E[i + j + 1]);
+            E[i + K] = Chain::addc(E[i + K], 0);
+            Chain::mad_wide_cc(O[i], O[i + 1], a[1], b[i], O[i], O[i + 1]);
+#pragma unroll
+            for (int j = 3; j < K; j += 2) Chain::madc_wide_cc(O[i + j - 1], O[i + j], a[j], b[i], O[i + j - 1], O[i + j]);
+            O[i + K] = Chain::addc(O[i + K], 0);
+        }
+    }
+    out[0] = E[0];
+    out[1] = Chain::add_cc(E[1], O[0]);
+#pragma unroll
+    for (int k = 2; k < 2 * K - 1; ++k) out[k] = Chain::addc_cc(E[k], O[k - 1]);
+    out[2 * K - 1] = Chain::addc(E[2 * K - 1], O[2 * K - 2]);
+}
+
+// out[2N] = a^2: the N(N-1)/2 off-diagonal products once, doubled, plus the N squares on the
+// diagonal -- N(N+1)/2 IMADs (78 for Fq) instead of N^2.
+template <int N>
+SONIC_HD void wide_sqr(uint32_t* out, const uint32_t* a) {
+    static_assert(N % 2 == 0, "even limb count");
+    uint32_t E[2 * N + 2], O[2 * N + 2];  // O[k] holds limb k+1
+#pragma unroll
+    for (int k = 0; k < 2 * N + 2; ++k) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+    for (int i = 0; i < N - 1; ++i) {
+        // a[i] * a[j], j > i: position i+j; j = i+1, i+3, .. are odd positions -> O[i+j-1]
+        Chain::mad_wide_cc(O[2 * i], O[2 * i + 1], a[i + 1], a[i], O[2 * i], O[2 * i + 1]);
+        int top = 2 * i;
+#pragma unroll
+        for (int j = i + 3; j < N; j += 2) {
+            Chain::madc_wide_cc(O[i + j - 1], O[i + j], a[j], a[i], O[i + j - 1], O[i + j]);
+            top = i + j - 1;
+        }
+        O[top + 2] = Chain::addc(O[top + 2], 0);
+        // j = i+2, i+4, .. are even positions -> E[i+j]
+        if (i + 2 < N) {
+            Chain::mad_wide_cc(E[2 * i + 2], E[2 * i + 3], a[i + 2], a[i], E[2 * i + 2], E[2 * i + 3]);
+            int etop = 2 * i + 2;
+#pragma unroll
+            for (int j = i + 4; j < N; j += 2) {
+                Chain::madc_wide_cc(E[i + j], E[i + j + 1], a[j], a[i], E[i + j], E[i + j + 1]);
+                etop = i + j;
+            }
+            E[etop + 2] = Chain::addc(E[etop + 2], 0);
+        }
+    }
+    // S = E + (O << 32): the off-diagonal half
+    uint32_t S[2 * N];
+    S[0] = E[0];
+    S[1] = Chain::add_cc(E[1], O[0]);
+#pragma unroll
+    for (int k = 2; k < 2 * N - 1; ++k) S[k] = Chain::addc_cc(E[k], O[k - 1]);
+    S[2 * N - 1] = Chain::addc(E[2 * N - 1], O[2 * N - 2]);
+    // out = 2*S + sum_i a_i^2 << 64 i
+    uint32_t lo, hi;
+    Chain::mul_wide(lo, hi, a[0], a[0]);
+    out[0] = Chain::add_cc(lo, S[0] << 1);
+    out[1] = Chain::addc_cc(hi, (S[1] << 1) | (S[0] >> 31));
+#pragma unroll
+    for (int i = 1; i < N; ++i) {
+        Chain::mul_wide(lo, hi, a[i], a[i]);
+        out[2 * i] = Chain::addc_cc(lo, (S[2 * i] << 1) | (S[2 * i - 1] >> 31));
+        out[2 * i + 1] = Chain::addc_cc(hi, (S[2 * i + 1] << 1) | (S[2 * i] >> 31));
+    }
+}
+
+// out[2N] = a * b by one level of Karatsuba over halves of K = N/2 limbs
+template <int N>
+SONIC_HD void wide_mul_karatsuba(uint32_t* out, const uint32_t* a, const uint32_t* b) {
+    constexpr int K = N / 2;
+    static_assert(N % 4 == 0, "halves must have an even limb count");
+    uint32_t z2[2 * K], sa[K], sb[K], zm[2 * K + 1];
+    wide_mul<K>(out, a, b);            // z0 -> out[0 .. 2K)
+    wide_mul<K>(z2, a + K, b + K);     // z2
+    // sa = a0 + a1, sb = b0 + b1 with carry bits ca, cb
+    sa[0] = Chain::add_cc(a[0], a[K]);
+#pragma unroll
+    for (int k = 1; k < K; ++k) sa[k] = Chain::addc_cc(a[k], a[K + k]);
+    const uint32_t ca = Chain::addc(0, 0);
+    sb[0] = Chain::add_cc(b[0], b[K]);
+#pragma unroll
+    for (int k = 1; k < K; ++k) sb[k] = Chain::addc_cc(b[k], b[K + k]);
+    const uint32_t cb = Chain::addc(0, 0);
+    wide_mul<K>(zm, sa, sb);
+    // zm += (ca ? sb : 0) << 32K  +  (cb ? sa : 0) << 32K  +  (ca & cb) << 64K
+    const uint32_t ma = 0u - ca, mb = 0u - cb;
+    zm[K] = Chain::add_cc(zm[K], sb[0] & ma);
+#pragma unroll
+    for (int k = 1; k < K; ++k) zm[K + k] = Chain::addc_cc(zm[K + k], sb[k] & ma);
+    zm[2 * K] = Chain::addc(ca & cb, 0);
+    zm[K] = Chain::add_cc(zm[K], sa[0] & mb);
+#pragma unroll
+    for (int k = 1; k < K; ++k) zm[K + k] = Chain::addc_cc(zm[K + k], sa[k] & mb);
+    zm[2 * K] = Chain::addc(zm[2 * K], 0);
+    // z1 = zm - z0 - z2  (non-negative, 2K+1 limbs)
+    zm[0] = Chain::sub_cc(zm[0], out[0]);
+#pragma unroll
+    for (int k = 1; k < 2 * K; ++k) zm[k] = Chain::subc_cc(zm[k], out[k]);
+    zm[2 * K] = Chain::subc(zm[2 * K], 0);
+    zm[0] = Chain::sub_cc(zm[0], z2[0]);
+#pragma unroll
+    for (int k = 1; k < 2 * K; ++k) zm[k] = Chain::subc_cc(zm[k], z2[k]);
+    zm[2 * K] = Chain::subc(zm[2 * K], 0);
+    // out = z0 + z1 << 32K + z2 << 64K
+#pragma unroll
+    for (int k = 0; k < 2 * K; ++k) out[2 * K + k] = z2[k];
+    out[K] = Chain::add_cc(out[K], zm[0]);
+#pragma unroll
+    for (int k = 1; k <= 2 * K; ++k) out[K + k] = Chain::addc_cc(out[K + k], zm[k]);
+#pragma unroll
+    for (int k = 3 * K + 1; k < 4 * K - 1; ++k) out[k] = Chain::addc_cc(out[k], 0);
+    out[4 * K - 1] = Chain::addc(out[4 * K - 1], 0);
+}
+
+// One reduction row on a sliding window: on entry `pe` is the even-aligned accumulator with
+// pe[0] == 0 and `po` the odd-aligned one; the window moves down one limb, `t` (the next limb of
+// the wide operand) enters at the top, and m*p is added so that the new low limb vanishes.
+// On exit the even-aligned accumulator is `po`, the odd-aligned one `pe`.
+template <class P>
+SONIC_HD void mont_reduce_next(uint32_t* pe, uint32_t* po, uint32_t t) {
+    constexpr int N = P::N;
+    po[0] = Chain::add_cc(po[0], pe[1]);  // carry has the weight of the new odd limb 0
+    const uint32_t m = po[0] * P::INV;
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) Chain::madc_wide_cc(pe[j], pe[j + 1], P::P(j + 1), m, pe[j + 2], pe[j + 3]);
+    Chain::madc_wide_cc(pe[N - 2], pe[N - 1], P::P(N - 1), m, t, 0);  // the top odd slot is free: t goes there
+    Chain::mad_wide_cc(po[0], po[1], P::P(0), m, po[0], po[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) Chain::madc_wide_cc(po[j], po[j + 1], P::P(j), m, po[j], po[j + 1]);
+    pe[N - 1] = Chain::addc(pe[N - 1], 0);
+}
+
+// Montgomery reduction of a 2N-limb value T < p * 2^(32N) * (small): returns T / R mod p, < 2p
+// before the final conditional subtraction (callers with larger T pass extra_sub = true).
+template <class P>
+SONIC_HD Fp<P> mont_reduce_wide(const uint32_t* T, bool extra_sub = false) {
+    constexpr int N = P::N;
+    uint32_t ev[N], od[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) { ev[k] = T[k]; od[k] = 0; }
+    mont_reduce_row<P>(ev, od);
+#pragma unroll
+    for (int i = 1; i < N; i += 2) {
+        mont_reduce_next<P>(ev, od, T[N + i - 1]);              // even-aligned now in od
+        if (i + 1 < N) mont_reduce_next<P>(od, ev, T[N + i]);  // back in ev
+    }
+    // N even: even-aligned accumulator is `od` (od[0] == 0), odd-aligned `ev`; the last limb enters at the top
+    Fp<P> r;
+    r.l[0] = Chain::add_cc(od[1], ev[0]);
+#pragma unroll
+    for (int k = 1; k < N - 1; ++k) r.l[k] = Chain::addc_cc(od[k + 1], ev[k]);
+    r.l[N - 1] = Chain::addc(ev[N - 1], T[2 * N - 1]);
+    fp_reduce_once(r);
+    if (extra_sub) fp_reduce_once(r);
+    return r;
+}
+
+template <class P>
+SONIC_HD Fp<P> fp_mul_karatsuba(const Fp<P>& a, const Fp<P>& b) {
+    uint32_t T[2 * P::N];
+    wide_mul_karatsuba<P::N>(T, a.l, b.l);
+    return mont_reduce_wide<P>(T);
+}
+
+// a*b + c*d with a single reduction.  Inputs reduced; 2p^2 + R p < 2 p R for both fields
+// (p / R < 1/2), so the result is < 2p before the conditional subtraction.
+#ifndef SONIC_WIDE_KARATSUBA
+#define SONIC_WIDE_KARATSUBA 0
+#endif
+template <class P>
+SONIC_HD Fp<P> fp_mul_add2(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
+    constexpr int N = P::N;
+    uint32_t T[2 * N], U[2 * N];
+#if SONIC_WIDE_KARATSUBA
+    wide_mul_karatsuba<N>(T, a.l, b.l);
+    wide_mul_karatsuba<N>(U, c.l, d.l);
+#else
+    wide_mul<N>(T, a.l, b.l);
+    wide_mul<N>(U, c.l, d.l);
+#endif
+    T[0] = Chain::add_cc(T[0], U[0]);
+#pragma unroll
+    for (int k = 1; k < 2 * N - 1; ++k) T[k] = Chain::addc_cc(T[k], U[k]);
+    T[2 * N - 1] = Chain::addc(T[2 * N - 1], U[2 * N - 1]);
+    return mont_reduce_wide<P>(T);
+}
+
+// a*b - c*d
+template <class P>
+SONIC_HD Fp<P> fp_mul_sub2(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
+    return fp_mul_add2(a, b, fp_neg(c), d);
+}
+
+// which multiplier `fp_mul` is: 0 interleaved CIOS (unrolled), 1 the same rolled, 2 Karatsuba + wide reduction
+#ifndef SONIC_MUL_VARIANT
+#define SONIC_MUL_VARIANT 0
 #endif
 
 template <class P>
 SONIC_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
-#if SONIC_MUL_ROLLED
+#if SONIC_MUL_VARIANT == 1
     return fp_mul_rolled(a, b);
+#elif SONIC_MUL_VARIANT == 2
+    return fp_mul_karatsuba(a, b);
 #else
     return fp_mul_unrolled(a, b);
 #endif
 }
 
+// 0: squaring is a multiplication; 1: half-product squaring + wide reduction
+#ifndef SONIC_SQR_WIDE
+#define SONIC_SQR_WIDE 1
+#endif
 template <class P>
-SONIC_HD Fp<P> fp_sqr(const Fp<P>& a) { return fp_mul(a, a); }
+SONIC_HD Fp<P> fp_sqr(const Fp<P>& a) {
+#if SONIC_SQR_WIDE
+    uint32_t T[2 * P::N];
+    wide_sqr<P::N>(T, a.l);
+    return mont_reduce_wide<P>(T);
+#else
+    return fp_mul(a, a);
+#endif
+}
 
 // canonical <-> Montgomery
 template <class P>

@@ -55,7 +55,7 @@ SONIC_HD G1XYZZ g1_mdbl(const G1Affine& a) {
     Fq M = fp_add(fp_dbl(X2), X2);
     G1XYZZ r;
     r.x = fp_sub(fp_sqr(M), fp_dbl(S));
-    r.y = fp_sub(fp_mul(M, fp_sub(S, r.x)), fp_mul(W, a.y));
+    r.y = fp_mul_sub2(M, fp_sub(S, r.x), W, a.y);
     r.zz = V;
     r.zzz = W;
     return r;
@@ -71,7 +71,7 @@ SONIC_HD G1XYZZ g1_dbl(const G1XYZZ& p) {
     Fq M = fp_add(fp_dbl(X2), X2);
     G1XYZZ r;
     r.x = fp_sub(fp_sqr(M), fp_dbl(S));
-    r.y = fp_sub(fp_mul(M, fp_sub(S, r.x)), fp_mul(W, p.y));
+    r.y = fp_mul_sub2(M, fp_sub(S, r.x), W, p.y);
     r.zz = fp_mul(V, p.zz);
     r.zzz = fp_mul(W, p.zzz);
     return r;
@@ -95,7 +95,7 @@ SONIC_HD void g1_madd(G1XYZZ& acc, const G1Affine& a) {
     Fq PPP = fp_mul(P, PP);
     Fq Q = fp_mul(acc.x, PP);
     Fq X3 = fp_sub(fp_sub(fp_sqr(R), PPP), fp_dbl(Q));
-    Fq Y3 = fp_sub(fp_mul(R, fp_sub(Q, X3)), fp_mul(acc.y, PPP));
+    Fq Y3 = fp_mul_sub2(R, fp_sub(Q, X3), acc.y, PPP);  // R*(Q-X3) - Y1*PPP, one reduction
     acc.x = X3;
     acc.y = Y3;
     acc.zz = fp_mul(acc.zz, PP);
@@ -121,7 +121,7 @@ SONIC_HD void g1_add(G1XYZZ& acc, const G1XYZZ& b) {
     Fq PPP = fp_mul(P, PP);
     Fq Q = fp_mul(U1, PP);
     Fq X3 = fp_sub(fp_sub(fp_sqr(R), PPP), fp_dbl(Q));
-    Fq Y3 = fp_sub(fp_mul(R, fp_sub(Q, X3)), fp_mul(S1, PPP));
+    Fq Y3 = fp_mul_sub2(R, fp_sub(Q, X3), S1, PPP);  // one reduction for the two products
     acc.x = X3;
     acc.y = Y3;
     acc.zz = fp_mul(fp_mul(acc.zz, b.zz), PP);

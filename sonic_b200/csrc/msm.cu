@@ -52,6 +52,33 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__
     // index selects the table level instead
     uint32_t gb0 = level_stride ? (uint32_t)j * B : (uint32_t)j * (uint32_t)W * B;
     const uint32_t gb_step = level_stride ? 0u : B;
+    if (W <= 16) {
+        // all digits first, then all atomics back to back (independent, so their latencies overlap)
+        uint32_t gb[16], val[16];
+#pragma unroll
+        for (int w = 0; w < 16; ++w) {
+            gb[w] = 0xffffffffu;
+            if (w < W) {
+                int32_t d = sd.next();
+                if (d != 0) {
+                    uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+                    gb[w] = gb0 + (uint32_t)w * gb_step + mag - 1;
+                    val[w] = (pid + (uint32_t)w * level_stride) | (d < 0 ? 0x80000000u : 0u);
+                }
+            }
+        }
+        if (SCATTER) {
+            uint32_t pos[16];
+#pragma unroll
+            for (int w = 0; w < 16; ++w) pos[w] = gb[w] != 0xffffffffu ? atomicAdd(&counters[gb[w]], 1u) : 0u;
+#pragma unroll
+            for (int w = 0; w < 16; ++w) if (gb[w] != 0xffffffffu) entries[pos[w]] = val[w];
+        } else {
+#pragma unroll
+            for (int w = 0; w < 16; ++w) if (gb[w] != 0xffffffffu) atomicAdd(&counters[gb[w]], 1u);
+        }
+        return;
+    }
     for (int w = 0; w < W; ++w, gb0 += gb_step, pid += level_stride) {
         int32_t d = sd.next();
         if (d == 0) continue;
@@ -328,7 +355,7 @@ static MsmPlan msm_plan(const Ctx& cx, uint32_t n_tot, int M, const MsmTables& t
     // offset multiple and the block tree) on top of 2 per bucket, so K is as large as the
     // machine fill allows
     uint64_t all_buckets = (uint64_t)p.GB;
-    uint64_t kfill = all_buckets / ((uint64_t)cx.sm_count * 256 * 2);
+    uint64_t kfill = all_buckets / ((uint64_t)cx.sm_count * MSM_RED_THREADS);  // about one block per SM
     p.K = (uint32_t)kfill;
     if (p.K < 8) p.K = 8;
     if (p.K > 64) p.K = 64;

@@ -230,16 +230,29 @@ __global__ void k_ntt_params(uint32_t logL, Fr* __restrict__ params) {
 }
 
 
+// Twiddle tables depend only on the length: they are built once per length and stay resident
+// (outside the per-call arena) for the life of the context.
 NttPlan ntt_prepare(Ctx& cx, uint32_t logL) {
+    auto it = cx.ntt_cache.find(logL);
+    if (it != cx.ntt_cache.end()) {
+        NttPlan p;
+        p.logL = logL;
+        p.params = (Fr*)it->second;
+        p.tw = p.params + 4;
+        p.twi = p.tw + (logL ? (1ull << (logL - 1)) : 1);
+        return p;
+    }
     NttPlan p;
     p.logL = logL;
     const uint64_t half = logL ? (1ull << (logL - 1)) : 1;
-    p.params = cx.arena.get<Fr>(3);
-    Fr* tabs = cx.arena.get<Fr>(2 * half);
-    p.tw = tabs;
-    p.twi = tabs + half;
+    Fr* mem = nullptr;
+    SONIC_CUDA(cudaMalloc((void**)&mem, (4 + 2 * half) * sizeof(Fr)));
+    cx.ntt_cache[logL] = mem;
+    p.params = mem;
+    p.tw = mem + 4;
+    p.twi = p.tw + half;
     SONIC_LAUNCH(k_ntt_params, 1, 32, 0, logL, p.params);
-    SONIC_LAUNCH(k_pow_tables, dim3(div_up(div_up(half, POW_RUN), 128), 2), 128, 0, p.params, tabs, half, half);
+    SONIC_LAUNCH(k_pow_tables, dim3(div_up(div_up(half, POW_RUN), 128), 2), 128, 0, p.params, p.tw, half, half);
     return p;
 }
 

@@ -96,14 +96,16 @@ __global__ void __launch_bounds__(256) k_build_suy_pm(const Fr* __restrict__ ut,
     (void)Q;
 }
 
-// Y^(n+q) slots: sum_i u^-i wL[q][i] + u^i wR[q][i] + u^(i+n) wO[q][i]; one block per q
+// Y^(n+q) slots: sum_i u^-i wL[q][i] + u^i wR[q][i] + u^(i+n) wO[q][i].
+// grid = (SUY_PARTS, Q): every block sums a slice of i into partial[q][part]; k_build_suy_fin folds.
+constexpr int SUY_PARTS = 32;
 __global__ void __launch_bounds__(256) k_build_suy_dot(const Fr* __restrict__ wL, const Fr* __restrict__ wR, const Fr* __restrict__ wO,
                                                        uint32_t n, const Fr* __restrict__ ut, const Fr* __restrict__ ui,
-                                                       Fr* __restrict__ out) {
+                                                       Fr* __restrict__ partial) {
     __shared__ Fr smem[8];
-    const uint32_t q = blockIdx.x;  // 0-based
+    const uint32_t q = blockIdx.y;  // 0-based
     Fr acc = Fr::zero();
-    for (uint32_t i0 = threadIdx.x; i0 < n; i0 += 256) {
+    for (uint32_t i0 = blockIdx.x * 256 + threadIdx.x; i0 < n; i0 += 256 * SUY_PARTS) {
         const uint32_t i = i0 + 1;
         const size_t w = (size_t)q * n + i0;
         acc = fp_add(acc, fp_mul(ui[i], wL[w]));
@@ -123,8 +125,16 @@ __global__ void __launch_bounds__(256) k_build_suy_dot(const Fr* __restrict__ wL
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 8; ++w) acc = fp_add(acc, smem[w]);
-        out[2 * n + 1 + q] = acc;  // exponent n + (q+1)
+        partial[q * SUY_PARTS + blockIdx.x] = acc;
     }
+}
+
+__global__ void k_build_suy_fin(const Fr* __restrict__ partial, uint32_t n, uint32_t Q, Fr* __restrict__ out) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    Fr acc = partial[q * SUY_PARTS];
+    for (int k = 1; k < SUY_PARTS; ++k) acc = fp_add(acc, partial[q * SUY_PARTS + k]);
+    out[2 * n + 1 + q] = acc;  // exponent n + (q+1)
 }
 
 // derived scalars: pts[] = the evaluation points (Montgomery), pts[np..2np) their inverses
@@ -361,7 +371,11 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
     suy.mont = ar.get<Fr>(suy.len);
     suy.canon = ar.get<Fr>(suy.len);
     SONIC_LAUNCH(k_build_suy_pm, div_up(2 * n + 1, 256), 256, 0, fwd(PT_U), n, Q, suy.mont);
-    SONIC_LAUNCH(k_build_suy_dot, Q, 256, 0, circ->wL(), circ->wR(), circ->wO(), n, fwd(PT_U), inv(PT_U), suy.mont);
+    {
+        Fr* part = ar.get<Fr>((size_t)Q * SUY_PARTS);
+        SONIC_LAUNCH(k_build_suy_dot, dim3(SUY_PARTS, Q), 256, 0, circ->wL(), circ->wR(), circ->wO(), n, fwd(PT_U), inv(PT_U), part);
+        SONIC_LAUNCH(k_build_suy_fin, div_up(Q, 64), 64, 0, part, n, Q, suy.mont);
+    }
     fr_from_mont(cx, suy.mont, suy.canon, suy.len);
 
     // ---- r'(X,1), t(X,y) ------------------------------------------------------------------------

@@ -26,6 +26,44 @@ void ht_fq_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     }
     st(out, r);
 }
+// op: 0 unrolled CIOS, 1 rolled CIOS, 2 Karatsuba + wide reduction, 3 a*b + c*d (one reduction), 4 a*b - c*d
+void ht_fq_mulvar(int op, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* out) {
+    Fq x = ld<Fq>(a), y = ld<Fq>(b), z = ld<Fq>(c), w = ld<Fq>(d), r;
+    switch (op) {
+        case 0: r = fp_mul_unrolled(x, y); break;
+        case 1: r = fp_mul_rolled(x, y); break;
+        case 2: r = fp_mul_karatsuba(x, y); break;
+        case 3: r = fp_mul_add2(x, y, z, w); break;
+        default: r = fp_mul_sub2(x, y, z, w); break;
+    }
+    st(out, r);
+}
+void ht_fr_mulvar(int op, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* out) {
+    Fr x = ld<Fr>(a), y = ld<Fr>(b), z = ld<Fr>(c), w = ld<Fr>(d), r;
+    switch (op) {
+        case 0: r = fp_mul_unrolled(x, y); break;
+        case 1: r = fp_mul_rolled(x, y); break;
+        case 2: r = fp_mul_karatsuba(x, y); break;
+        case 3: r = fp_mul_add2(x, y, z, w); break;
+        default: r = fp_mul_sub2(x, y, z, w); break;
+    }
+    st(out, r);
+}
+// raw wide product of two K-limb numbers (K = 4 or 6) and of two 2K-limb numbers by Karatsuba
+void ht_wide_sqr(int N, const uint32_t* a, uint32_t* out) {
+    if (N == 12) wide_sqr<12>(out, a);
+    else if (N == 8) wide_sqr<8>(out, a);
+    else if (N == 6) wide_sqr<6>(out, a);
+    else wide_sqr<4>(out, a);
+}
+void ht_wide_mul(int K, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    if (K == 6) wide_mul<6>(out, a, b);
+    else if (K == 4) wide_mul<4>(out, a, b);
+    else if (K == 12) wide_mul_karatsuba<12>(out, a, b);
+    else if (K == 112) wide_mul<12>(out, a, b);
+    else if (K == 108) wide_mul<8>(out, a, b);
+    else wide_mul_karatsuba<8>(out, a, b);
+}
 void ht_fr_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     Fr x = ld<Fr>(a), y = ld<Fr>(b), r;
     switch (op) {

@@ -106,3 +106,36 @@ def test_signed_digit_recoding(host):
             assert host.ht_recode(_arr(s, 8), c, d) == W
             assert sum(int(d[j]) << (c * j) for j in range(W)) % R == s
             assert all(abs(int(d[j])) <= 1 << (c - 1) for j in range(W))
+
+
+def test_wide_products_and_multiplier_variants(host):
+    """wide_mul / wide_sqr / Karatsuba (unreduced 2N-limb products, extreme limb patterns included)
+    and every Montgomery multiplier variant, plus the fused a*b +- c*d with a single reduction."""
+    rng = random.Random(34)
+
+    def pat(n):
+        return sum(rng.choice([0, 0xFFFFFFFF, 0x80000000, rng.getrandbits(32)]) << (32 * i) for i in range(n))
+
+    for K, n in ((4, 4), (6, 6), (8, 8), (12, 12), (112, 12), (108, 8)):
+        full = (1 << (32 * n)) - 1
+        cases = [(full, full), (full, 1), (0, full), (full - 1, full)] + [(pat(n), pat(n)) for _ in range(1500)]
+        for a, b in cases:
+            out = (ctypes.c_uint32 * (2 * n))()
+            host.ht_wide_mul(K, _arr(a, n), _arr(b, n), out)
+            assert from_limbs(out) == a * b, (K, hex(a), hex(b))
+    for n in (4, 6, 8, 12):
+        full = (1 << (32 * n)) - 1
+        for a in [full, 0, 1, full - 1, 1 << (32 * n - 1)] + [pat(n) for _ in range(1500)]:
+            out = (ctypes.c_uint32 * (2 * n))()
+            host.ht_wide_sqr(n, _arr(a, n), out)
+            assert from_limbs(out) == a * a, (n, hex(a))
+    for fn, n, p in ((host.ht_fq_mulvar, 12, Q), (host.ht_fr_mulvar, 8, R)):
+        Ri = pow(1 << (32 * n), -1, p)
+        edge = [0, 1, p - 1, (p - 1) // 2]
+        samples = [(a, b, c, d) for a in edge for b in edge for c in (0, p - 1) for d in (1, p - 1)]
+        samples += [tuple(rng.randrange(p) for _ in range(4)) for _ in range(1500)]
+        for a, b, c, d in samples:
+            for op, want in ((0, a * b), (1, a * b), (2, a * b), (3, a * b + c * d), (4, a * b - c * d)):
+                out = (ctypes.c_uint32 * n)()
+                fn(op, _arr(a, n), _arr(b, n), _arr(c, n), _arr(d, n), out)
+                assert from_limbs(out) == want * Ri % p, (op, n)
