@@ -7,6 +7,8 @@
 //   power tables      base^k                      (Utils.hs:18 `pow`, CommitmentScheme.hs:43 `eval`)
 //   open              f(z) and (f(X)-f(z))/(X-z)  (CommitmentScheme.hs:43-44)
 //   NTT               radix-2 over Fr, 2-adicity 32, for t(X,y) (Constraints.hs:61)
+#include <vector>
+
 #include "internal.h"
 
 namespace sonic {
@@ -180,30 +182,71 @@ __global__ void __launch_bounds__(OPEN_THREADS) k_open_quotient(const OpenJob* _
 }
 
 // ---- NTT ------------------------------------------------------------------------------------
-// Radix-2, in place.  Forward = decimation in frequency (natural in, bit-reversed out);
-// inverse = decimation in time on the bit-reversed data (natural out), so a cyclic
-// convolution needs no permutation.  tw[k] = omega^k, k < L/2 (omega^-k for the inverse).
-__global__ void __launch_bounds__(256) k_ntt_dif_stage(Fr* __restrict__ a, const Fr* __restrict__ tw, uint32_t logL, uint32_t stage) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // butterfly index < L/2
-    if (i >= (1u << (logL - 1))) return;
-    const uint32_t half = 1u << (logL - 1 - stage);
-    const uint32_t j = i & (half - 1);
-    const uint32_t lo = ((i - j) << 1) + j;
-    const Fr u = a[lo], v = a[lo + half];
-    a[lo] = fp_add(u, v);
-    a[lo + half] = fp_mul(fp_sub(u, v), tw[j << stage]);
-}
+// Radix-2 over Fr (2-adicity 32), in place.  Forward = decimation in frequency (natural in,
+// bit-reversed out); inverse = decimation in time on the bit-reversed data (natural out), so a
+// cyclic convolution needs no permutation.  tw[k] = omega^k, k < L/2 (omega^-k for the inverse).
+//
+// Butterflies are staged through shared memory: one launch runs `nb` consecutive stages on
+// tiles of 2^nb x C elements (<= 1024 elements = 32 KB), where the 2^nb rows are the index
+// bits those stages touch and the C columns are adjacent low-order indices, so that every
+// global access is a run of C consecutive 32-byte elements.  L = 2^19 takes 3 launches per
+// transform instead of 19 (stages 6 + 6 + 7 forward; 10 + 6 + 3 inverse).
+constexpr int NTT_TILE_LOG = 10;
+constexpr int NTT_THREADS = 512;
 
-__global__ void __launch_bounds__(256) k_ntt_dit_stage(Fr* __restrict__ a, const Fr* __restrict__ tw, uint32_t logL, uint32_t stage) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (1u << (logL - 1))) return;
-    const uint32_t half = 1u << stage;  // stage 0 first: smallest butterflies
-    const uint32_t j = i & (half - 1);
-    const uint32_t lo = ((i - j) << 1) + j;
-    const Fr u = a[lo];
-    const Fr v = fp_mul(a[lo + half], tw[j << (logL - 1 - stage)]);
-    a[lo] = fp_add(u, v);
-    a[lo + half] = fp_sub(u, v);
+template <bool INVERSE>
+__global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(Fr* __restrict__ a, const Fr* __restrict__ tw, uint32_t logL,
+                                                          uint32_t lowbit, uint32_t nb, uint32_t logC,
+                                                          const Fr* __restrict__ scale) {
+    __shared__ Fr tile[1 << NTT_TILE_LOG];
+    const uint32_t C = 1u << logC;
+    const uint32_t tile_elems = 1u << (nb + logC);
+    // block -> (hi, lg): bits above the staged ones, and the group of C low-order columns
+    const uint32_t lg_count_log = lowbit - logC;
+    const uint32_t hi = blockIdx.x >> lg_count_log;
+    const uint32_t lg = blockIdx.x & ((1u << lg_count_log) - 1);
+    const uint32_t gbase = (hi << (lowbit + nb)) | (lg << logC);
+    for (uint32_t t = threadIdx.x; t < tile_elems; t += NTT_THREADS) {
+        const uint32_t k = t >> logC, c = t & (C - 1);
+        tile[t] = a[gbase | (k << lowbit) | c];
+    }
+    __syncthreads();
+    const uint32_t nbf = tile_elems >> 1;
+    for (uint32_t ls = 0; ls < nb; ++ls) {
+        // forward: large strides first (row bit nb-1-ls, global stage s = logL-lowbit-nb+ls, half = L >> (s+1));
+        // inverse: small strides first (row bit ls, global stage s = lowbit+ls, half = 1 << s)
+        const uint32_t kbit = INVERSE ? ls : nb - 1 - ls;
+        const uint32_t halfk = 1u << kbit;
+        const uint32_t s = INVERSE ? lowbit + ls : logL - lowbit - nb + ls;
+        const uint32_t ghalf_log = INVERSE ? s : logL - 1 - s;
+        const uint32_t tw_shift = INVERSE ? logL - 1 - s : s;
+        for (uint32_t bf = threadIdx.x; bf < nbf; bf += NTT_THREADS) {
+            const uint32_t c = bf & (C - 1), kp = bf >> logC;
+            const uint32_t jk = kp & (halfk - 1);
+            const uint32_t klo = ((kp - jk) << 1) + jk;
+            const uint32_t tlo = (klo << logC) | c, thi = ((klo + halfk) << logC) | c;
+            const uint32_t glo = gbase | (klo << lowbit) | c;
+            const uint32_t j = glo & ((1u << ghalf_log) - 1);
+            const Fr w = tw[(size_t)j << tw_shift];
+            const Fr u = tile[tlo];
+            if (INVERSE) {
+                const Fr v = fp_mul(tile[thi], w);
+                tile[tlo] = fp_add(u, v);
+                tile[thi] = fp_sub(u, v);
+            } else {
+                const Fr v = tile[thi];
+                tile[tlo] = fp_add(u, v);
+                tile[thi] = fp_mul(fp_sub(u, v), w);
+            }
+        }
+        __syncthreads();
+    }
+    for (uint32_t t = threadIdx.x; t < tile_elems; t += NTT_THREADS) {
+        const uint32_t k = t >> logC, c = t & (C - 1);
+        Fr v = tile[t];
+        if (scale) v = fp_mul(v, *scale);
+        a[gbase | (k << lowbit) | c] = v;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_fr_mul_pointwise(Fr* __restrict__ a, const Fr* __restrict__ b, uint32_t n) {
@@ -256,17 +299,44 @@ NttPlan ntt_prepare(Ctx& cx, uint32_t logL) {
     return p;
 }
 
+// Splits the logL stages into passes: one contiguous pass of up to NTT_TILE_LOG stages on the
+// low bits, the remaining (strided) stages in groups of up to 6 with C = 1024 >> nb columns.
+struct NttPass { uint32_t lowbit, nb, logC; };
+static std::vector<NttPass> ntt_passes(uint32_t logL) {
+    std::vector<NttPass> v;  // ordered from the low bits up
+    const uint32_t nlow = logL < (uint32_t)NTT_TILE_LOG ? logL : (uint32_t)NTT_TILE_LOG;
+    v.push_back({0u, nlow, 0u});
+    uint32_t bit = nlow;
+    while (bit < logL) {
+        uint32_t nb = logL - bit < 6 ? logL - bit : 6;
+        uint32_t logC = NTT_TILE_LOG - nb;
+        if (logC > bit) logC = bit;
+        v.push_back({bit, nb, logC});
+        bit += nb;
+    }
+    return v;
+}
+
 void ntt_forward(const NttPlan& p, Fr* a) {
-    const uint32_t half = 1u << (p.logL - 1);
-    for (uint32_t s = 0; s < p.logL; ++s) SONIC_LAUNCH(k_ntt_dif_stage, div_up(half, 256), 256, 0, a, p.tw, p.logL, s);
+    if (p.logL == 0) return;
+    std::vector<NttPass> ps = ntt_passes(p.logL);
+    for (size_t i = ps.size(); i-- > 0;) {  // decimation in frequency: high bits first
+        const NttPass& q = ps[i];
+        const uint32_t blocks = 1u << (p.logL - q.nb - q.logC);
+        SONIC_LAUNCH(k_ntt_pass<false>, blocks, NTT_THREADS, 0, a, p.tw, p.logL, q.lowbit, q.nb, q.logC, (const Fr*)nullptr);
+    }
 }
 
 void ntt_inverse(const NttPlan& p, Fr* a) {
-    const uint32_t half = 1u << (p.logL - 1);
-    for (uint32_t s = 0; s < p.logL; ++s) SONIC_LAUNCH(k_ntt_dit_stage, div_up(half, 256), 256, 0, a, p.twi, p.logL, s);
-    SONIC_LAUNCH(k_fr_scale, div_up(2 * half, 256), 256, 0, a, p.params + 2, 2 * half);
+    if (p.logL == 0) return;
+    std::vector<NttPass> ps = ntt_passes(p.logL);
+    for (size_t i = 0; i < ps.size(); ++i) {  // decimation in time: low bits first; 1/L folded into the last store
+        const NttPass& q = ps[i];
+        const uint32_t blocks = 1u << (p.logL - q.nb - q.logC);
+        SONIC_LAUNCH(k_ntt_pass<true>, blocks, NTT_THREADS, 0, a, p.twi, p.logL, q.lowbit, q.nb, q.logC,
+                     i + 1 == ps.size() ? (const Fr*)(p.params + 2) : (const Fr*)nullptr);
+    }
 }
-
 
 // ---- host launchers ---------------------------------------------------------------------------
 void fr_to_mont(Ctx& cx, const Fr* in, Fr* out, uint64_t n, uint32_t* bad_flag) {
