@@ -35,7 +35,8 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 CANON_WINDOW = 16                      # canonical c = 16 => W = 16 bucket insertions / point
-LMAC_PER_MADD = 3000                   # 10 Fq multiplications x 300 LMAC
+LMAC_PER_MADD = 3000                   # canonical: 10 Fq multiplications x 300 LMAC
+EXEC_LMAC_PER_MADD = 6 * 300 + 2 * 234 + 444   # executed: 6 mul, 2 half-product squarings, 1 fused a*b-c*d (2 products, 1 reduction)
 CANON_LMAC_PER_POINT = 16 * LMAC_PER_MADD
 
 
@@ -167,6 +168,7 @@ def main() -> None:
     ap.add_argument("--no-sweep", action="store_true", help="skip the standalone MSM sweep (config 3)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--sweep-max", type=int, default=24)
+    ap.add_argument("--config5", action="store_true", help="also run BASELINE config 5: SRS.new d=2^22, then 64 proofs at n=2^14 spread over the ranks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -281,6 +283,11 @@ def main() -> None:
         p_e2e = step_e2e()
     if p_res != p_e2e:
         raise SystemExit("resident and host-buffer proofs differ")
+    if world > 1:
+        # the sharded proof must be the single-GPU proof, byte for byte
+        capi.check(L.sonic_prove(srs._h, ch, hin, hin + n * 32, hin + 2 * n * 32, hrnd, out, len(out), ctypes.byref(written)))
+        if out.raw[:proof_size] != p_res:
+            raise SystemExit("sharded proof differs from the single-GPU proof")
     ev_ms, wall_ms, launches, proof = timed(step_resident, args.steps)
     stage = {k: sb.last_timing_ms(k) for k in ("msm", "msm.sort", "msm.accumulate", "msm.accumulate_kernel", "msm.reduce", "poly", "total",
                                                "msm.window_bits", "msm.windows", "msm.terms", "msm.entries", "msm.chunk", "msm.buckets")}
@@ -297,7 +304,7 @@ def main() -> None:
     acc_ms = stage["msm.accumulate_kernel"]
     shard_terms = stage["msm.terms"]                       # terms this rank's launch processed
     canon_lmac = shard_terms * CANON_LMAC_PER_POINT
-    exec_lmac = stage["msm.entries"] * LMAC_PER_MADD
+    exec_lmac = stage["msm.entries"] * EXEC_LMAC_PER_MADD
     achieved = canon_lmac / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else 0.0
     traffic = None
     tpath = sorted([os.path.join(ROOT, "profiles", f) for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_accumulate_traffic.json")] or [""])[-1]
@@ -367,12 +374,61 @@ def main() -> None:
                               "window_bits": sb.last_timing_ms("msm.window_bits")})
                 capi.check(L.sonic_dev_free(dsc))
 
+    # ---- BASELINE config 5: SRS.new at d = 2^22, then a batch of 64 independent proofs at n = 2^14 -------
+    config5 = None
+    if args.config5:
+        d5 = 1 << 22
+        barrier()
+        t0 = time.perf_counter()
+        srs5 = sb.SRS.new(d5, x, alpha)          # every rank builds its replica (the SRS is replicated)
+        torch.cuda.synchronize()
+        srs5_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+        srs5_dev_ms = max_over_ranks(sb.last_timing_ms("total"))
+        n5, total_proofs = 1 << 14, 64
+        c5 = synth.synthetic_circuit_bytes(n5, Q, seed=5)
+        ch5 = ctypes.c_void_p()
+        capi.check(L.sonic_circuit_load(n5, Q, c5["wL"].ctypes.data, c5["wR"].ctypes.data, c5["wO"].ctypes.data,
+                                        c5["cs"].ctypes.data, ctypes.byref(ch5)))
+        mine = [i for i in range(total_proofs) if i % world == rank]
+        rnds = [np.frombuffer(synth.ints_to_bytes([v or 1 for v in synth.fr_ints(500 + i, nr)]), dtype=np.uint8).copy() for i in mine]
+        o5 = ctypes.create_string_buffer(proof_size)
+
+        def batch():
+            for r5 in rnds:
+                capi.check(L.sonic_prove(srs5._h, ch5, c5["aL"].ctypes.data, c5["aR"].ctypes.data, c5["aO"].ctypes.data,
+                                         r5.ctypes.data, o5, proof_size, ctypes.byref(written)))
+        batch()
+        barrier()
+        capi.check(L.sonic_bench_mark(4))
+        batch()
+        capi.check(L.sonic_bench_mark(5))
+        b_ms = max_over_ranks(L.sonic_bench_elapsed_ms(4, 5))
+        barrier()
+        config5 = {"srs_new_d_2pow22_ms": {"wall": srs5_ms, "device": srs5_dev_ms, "points": 4 * d5 + 1,
+                                           "mpoints_per_s": (4 * d5 + 1) / (srs5_dev_ms * 1e-3) / 1e6, "precomputed_tables": False},
+                   "batch_64_proofs_n_2pow14": {"ms": b_ms, "proofs_per_s": total_proofs / (b_ms * 1e-3), "proofs_per_rank": len(mine),
+                                                "scaling": "weak (independent proofs, no exchange)"}}
+        L.sonic_circuit_free(ch5)
+        srs5.free()
+
     # ---- CPU baseline (rank 0, N = 1 only): the reference algorithm on one core --------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sample = 1 << 15
         rate, dt = cpu_sample(sample, 1, 7)
+        # context: a CPU bucket-method MSM on all host threads (not the reference's algorithm)
+        from oracle import cref
+        psample, pc = 1 << 16, 12
+        x_, a_ = synth.trapdoor()
+        if psample // 2 not in _TABLES:
+            _TABLES[psample // 2] = cref.srs_new(psample // 2, x_, a_, threads=host_threads())
+        pscal = synth.fr_bytes_fast(8, psample).tobytes()
+        tp = time.perf_counter()
+        cref.msm_pippenger(_TABLES[psample // 2][:96 * psample], pscal, psample, pc, host_threads())
+        pdt = time.perf_counter() - tp
         cpu = {"value": rate / 1e6, "unit": "Mpoints/s", "cores": 1, "kind": "port",
+               "pippenger_context": {"value": psample / pdt / 1e6, "unit": "Mpoints/s", "cores": host_threads(), "window_bits": pc,
+                                     "sample": "%d terms, %.1f s; plain windowed bucket method in C, NOT the reference's algorithm" % (psample, pdt)},
                "sample": "%d uniform-Fr terms, reference algorithm (double-and-add per term + fold, CommitmentScheme.hs:26-29) "
                          "in C (oracle/csrc/sonic_ref.c), %.1f s; the Haskell reference is single-threaded and cannot be built here" % (sample, dt),
                "extrapolated_prove_ms": 1e3 * terms / rate, "host_threads_available": host_threads()}
@@ -397,6 +453,7 @@ def main() -> None:
             "roofline": roofline,
             "cpu_baseline": cpu,
             "msm_sweep": sweep,
+            "config5": config5,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -70,6 +70,12 @@ int sonic_srs_new(uint64_t d, const uint8_t x[32], const uint8_t alpha[32], soni
 void sonic_srs_free(sonic_srs* srs);
 uint64_t sonic_srs_d(const sonic_srs* srs); /* srsD, src/Sonic/SRS.hs:12 */
 
+/* SRS persistence (the reference has no on-disk format: SRS.hs:11-22 derives nothing):
+ * the resident device arrays, precomputed levels included, as one file, so that a large setup is
+ * paid once per machine rather than once per process.  The trapdoor is never stored. */
+int sonic_srs_save(const sonic_srs* srs, const char* path);
+int sonic_srs_load(const char* path, sonic_srs** out);
+
 /* Element of gNegativeX/gPositiveX/gNegativeAlphaX/gPositiveAlphaX by exponent
  * (record fields, src/Sonic/SRS.hs:13-18).  family ALPHA, exponent 0 -> SONIC_ERR_SRS_TOO_SHORT. */
 int sonic_srs_g1(const sonic_srs* srs, int family, int64_t exponent, uint8_t out[48]);

@@ -29,6 +29,8 @@ def lib():
         L = ctypes.CDLL(LIB_PATH)
         L.ref_msm_naive.restype = None
         L.ref_msm_naive.argtypes = [c_void_p, c_void_p, c_uint64, c_int, c_void_p, c_void_p]
+        L.ref_msm_pippenger.restype = None
+        L.ref_msm_pippenger.argtypes = [c_void_p, c_void_p, c_uint64, c_int, c_int, c_void_p]
         L.ref_srs_new.restype = c_int
         L.ref_srs_new.argtypes = [c_uint64, c_void_p, c_void_p, c_int, c_void_p]
         L.ref_commit.restype = c_int
@@ -68,6 +70,13 @@ def msm_naive(points_raw, scalars, n: int, threads: int = 1, raw: bool = False) 
         lib().ref_msm_naive(_ptr(points_raw), _ptr(scalars), n, threads, None, out)
     else:
         lib().ref_msm_naive(_ptr(points_raw), _ptr(scalars), n, threads, out, None)
+    return out.raw
+
+
+def msm_pippenger(points_raw, scalars, n: int, c: int = 12, threads: int = 1) -> bytes:
+    """Bucket-method MSM on the CPU (context baseline, NOT the reference's algorithm)."""
+    out = ctypes.create_string_buffer(48)
+    lib().ref_msm_pippenger(_ptr(points_raw), _ptr(scalars), n, c, threads, out)
     return out.raw
 
 

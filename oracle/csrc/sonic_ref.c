@@ -317,6 +317,55 @@ void ref_msm_naive(const uint8_t* points_raw, const uint8_t* scalars, uint64_t n
     if (out_raw96) g1_to_raw(&acc, out_raw96);
 }
 
+/* ---------------------------------------------------------------- MSM, bucket method (context only) ---- */
+/* NOT the reference's algorithm: a plain windowed Pippenger on the CPU so that the GPU speed-up
+ * is not quoted against the naive fold alone ("B-pip").  One window per
+ * task; unsigned c-bit digits; threads split the windows. */
+typedef struct { const uint8_t* pts; const uint8_t* scal; uint64_t n; int c; int nwin; g1* win; } pip_ctx;
+static void pip_range(void* cv, uint64_t lo, uint64_t hi, int tid) {
+    (void)tid;
+    pip_ctx* p = (pip_ctx*)cv;
+    const uint64_t nb = ((uint64_t)1 << p->c) - 1;
+    g1* buckets = malloc(sizeof(g1) * nb);
+    for (uint64_t w = lo; w < hi; ++w) {
+        for (uint64_t b = 0; b < nb; ++b) buckets[b] = g1_inf();
+        const int bit = (int)w * p->c;
+        for (uint64_t i = 0; i < p->n; ++i) {
+            u64 k[NR + 1];
+            memcpy(k, p->scal + 32 * i, 32);
+            k[NR] = 0;
+            const int limb = bit >> 6, sh = bit & 63;
+            u64 dgt = k[limb] >> sh;
+            if (sh && limb + 1 <= NR) dgt |= k[limb + 1] << (64 - sh);
+            dgt &= nb;
+            if (!dgt) continue;
+            g1 pt = g1_from_raw(p->pts + 96 * i);
+            buckets[dgt - 1] = g1_add(buckets[dgt - 1], pt);
+        }
+        g1 run = g1_inf(), acc = g1_inf();
+        for (uint64_t b = nb; b-- > 0;) {
+            run = g1_add(run, buckets[b]);
+            acc = g1_add(acc, run);
+        }
+        p->win[w] = acc;
+    }
+    free(buckets);
+}
+void ref_msm_pippenger(const uint8_t* points_raw, const uint8_t* scalars, uint64_t n, int c, int threads, uint8_t* out48) {
+    pip_ctx p;
+    p.pts = points_raw; p.scal = scalars; p.n = n; p.c = c;
+    p.nwin = (255 + c - 1) / c;
+    p.win = malloc(sizeof(g1) * p.nwin);
+    parallel_for((uint64_t)p.nwin, threads, pip_range, &p);
+    g1 acc = g1_inf();
+    for (int w = p.nwin - 1; w >= 0; --w) {
+        for (int i = 0; i < c; ++i) acc = g1_dbl(acc);
+        acc = g1_add(acc, p.win[w]);
+    }
+    free(p.win);
+    g1_compress(&acc, out48);
+}
+
 /* ---------------------------------------------------------------- SRS.new ---- */
 typedef struct { uint64_t d; fr x, xinv, alpha; uint8_t* out; } srs_ctx;
 /* element index e in [0, 2*(2d+1)): family = e / (2d+1), exponent k = e % (2d+1) - d */

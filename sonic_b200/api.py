@@ -109,6 +109,17 @@ class SRS:
         check(lib().sonic_srs_new(d, _fr(x), _fr(alpha), ctypes.byref(h)))
         return SRS(h, d)
 
+    def save(self, path: str) -> None:
+        """Writes the resident arrays (precomputed levels included) to `path`; no trapdoor is stored."""
+        check(lib().sonic_srs_save(self._h, path.encode()))
+
+    @staticmethod
+    def load(path: str) -> "SRS":
+        capi.init()
+        h = c_void_p()
+        check(lib().sonic_srs_load(path.encode(), ctypes.byref(h)))
+        return SRS(h, int(lib().sonic_srs_d(h)))
+
     def _range(self, family: int, lo: int, count: int) -> List[G1Bytes]:
         out = ctypes.create_string_buffer(48 * count)
         check(lib().sonic_srs_g1_range(self._h, family, lo, count, out))

@@ -39,6 +39,8 @@ SYMBOLS = {
     "sonic_srs_new": (c_int, [c_uint64, _u8p, _u8p, POINTER(c_void_p)]),
     "sonic_srs_free": (None, [c_void_p]),
     "sonic_srs_d": (c_uint64, [c_void_p]),
+    "sonic_srs_save": (c_int, [c_void_p, c_char_p]),
+    "sonic_srs_load": (c_int, [c_char_p, POINTER(c_void_p)]),
     "sonic_srs_g1": (c_int, [c_void_p, c_int, c_int64, _u8p]),
     "sonic_srs_g1_range": (c_int, [c_void_p, c_int, c_int64, c_uint64, _u8p]),
     "sonic_commit": (c_int, [c_void_p, c_int64, c_int64, c_uint64, _u8p, _u8p]),

@@ -383,6 +383,86 @@ void sonic_srs_free(sonic_srs* srs) {
 
 uint64_t sonic_srs_d(const sonic_srs* srs) { return srs ? srs->d : 0; }
 
+// ---- SRS persistence: the resident arrays as one file --------------------
+namespace {
+struct SrsFileHeader {
+    char magic[8];       // "SONICSRS"
+    uint32_t version;    // 1
+    uint32_t pre_c;      // window bits of the precomputed levels (0 = level 0 only)
+    uint64_t d;
+    uint64_t levels;
+    uint64_t points_per_level;  // 2 * (2d + 1)
+};
+}  // namespace
+
+int sonic_srs_save(const sonic_srs* srs, const char* path) {
+    if (!srs || !path) return fail(SONIC_ERR_INVALID_ARG, "null argument");
+    return guarded([&](Ctx& cx) {
+        FILE* f = fopen(path, "wb");
+        if (!f) return fail(SONIC_ERR_INVALID_ARG, "cannot open %s for writing", path);
+        SrsFileHeader h;
+        memcpy(h.magic, "SONICSRS", 8);
+        h.version = 1;
+        h.pre_c = (uint32_t)srs->tables.c;
+        h.d = srs->d;
+        h.levels = srs->tables.c > 0 ? (uint64_t)srs->tables.W : 1;
+        h.points_per_level = 2 * srs->stride();
+        bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+        const size_t total = (size_t)h.levels * h.points_per_level * sizeof(G1Affine);
+        const size_t chunk = size_t(64) << 20;
+        uint8_t* stage = pinned(cx, chunk);
+        for (size_t off = 0; ok && off < total; off += chunk) {
+            const size_t nbytes = std::min(chunk, total - off);
+            SONIC_CUDA(cudaMemcpyAsync(stage, (const uint8_t*)srs->points + off, nbytes, cudaMemcpyDeviceToHost, cx.stream));
+            SONIC_CUDA(cudaStreamSynchronize(cx.stream));
+            ok = fwrite(stage, 1, nbytes, f) == nbytes;
+        }
+        ok = (fclose(f) == 0) && ok;
+        if (!ok) return fail(SONIC_ERR_INVALID_ARG, "short write to %s", path);
+        return (int)SONIC_OK;
+    });
+}
+
+int sonic_srs_load(const char* path, sonic_srs** out) {
+    if (!path || !out) return fail(SONIC_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    return guarded([&](Ctx& cx) {
+        FILE* f = fopen(path, "rb");
+        if (!f) return fail(SONIC_ERR_INVALID_ARG, "cannot open %s", path);
+        SrsFileHeader h;
+        if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "SONICSRS", 8) != 0 || h.version != 1 || h.d == 0 ||
+            h.d >= (1ull << 28) || h.points_per_level != 2 * (2 * h.d + 1) || h.levels == 0 || h.levels > 64 ||
+            (h.pre_c == 0 ? h.levels != 1 : h.levels != (255 + h.pre_c - 1) / h.pre_c)) {
+            fclose(f);
+            return fail(SONIC_ERR_INVALID_ARG, "%s is not an SRS file of this library", path);
+        }
+        sonic_srs* s = new sonic_srs;
+        s->d = h.d;
+        s->tables.c = (int)h.pre_c;
+        s->tables.W = h.pre_c ? (int)h.levels : 0;
+        s->tables.stride = (uint32_t)h.points_per_level;
+        const size_t total = (size_t)h.levels * h.points_per_level * sizeof(G1Affine);
+        cudaError_t e = cudaMalloc((void**)&s->points, total);
+        if (e != cudaSuccess) { fclose(f); delete s; throw CudaError{e, "cudaMalloc(srs)", __LINE__}; }
+        const size_t chunk = size_t(64) << 20;
+        uint8_t* stage = pinned(cx, chunk);
+        bool ok = true;
+        for (size_t off = 0; ok && off < total; off += chunk) {
+            const size_t nbytes = std::min(chunk, total - off);
+            ok = fread(stage, 1, nbytes, f) == nbytes;
+            if (ok) {
+                cudaError_t ce = cudaMemcpyAsync((uint8_t*)s->points + off, stage, nbytes, cudaMemcpyHostToDevice, cx.stream);
+                if (ce == cudaSuccess) ce = cudaStreamSynchronize(cx.stream);
+                if (ce != cudaSuccess) { fclose(f); cudaFree(s->points); delete s; throw CudaError{ce, "upload(srs)", __LINE__}; }
+            }
+        }
+        fclose(f);
+        if (!ok) { cudaFree(s->points); delete s; return fail(SONIC_ERR_INVALID_ARG, "%s is truncated", path); }
+        *out = s;
+        return (int)SONIC_OK;
+    });
+}
+
 int sonic_srs_g1_range(const sonic_srs* srs, int family, int64_t exponent, uint64_t count, uint8_t* out) {
     if (!srs || !out || (family != SONIC_FAMILY_PLAIN && family != SONIC_FAMILY_ALPHA)) return fail(SONIC_ERR_INVALID_ARG, "bad argument");
     const int64_t d = (int64_t)srs->d;

@@ -471,6 +471,29 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
     SONIC_CUDA(cudaMemsetAsync(viol, 0xff, 12 * (size_t)nm, st));
     std::vector<MsmJob> jobs(nm);
     std::vector<int64_t> slice_lo(nm, 0);
+    // Sharding over `world` ranks, two ways: whole MSMs are dealt to the ranks
+    // (longest first, to the least loaded rank) when that balances, so that sorting, bucket
+    // reduction and the tail shrink with the rank count too; otherwise every MSM is cut into
+    // `world` contiguous slices.  Both are deterministic functions of the sizes: all ranks agree.
+    std::vector<int> owner(nm, -1);
+    bool by_job = false;
+    if (sharded) {
+        std::vector<uint64_t> load(world, 0);
+        std::vector<uint32_t> order(nm);
+        for (uint32_t i = 0; i < nm; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return pm[a].len > pm[b].len; });
+        uint64_t total_len = 0;
+        for (uint32_t i : order) {
+            uint32_t best = 0;
+            for (uint32_t r = 1; r < world; ++r) if (load[r] < load[best]) best = r;
+            owner[i] = (int)best;
+            load[best] += pm[i].len;
+            total_len += pm[i].len;
+        }
+        uint64_t max_load = 0;
+        for (uint64_t l : load) max_load = std::max(max_load, l);
+        by_job = nm >= world && max_load * world <= total_len + total_len / 5;  // within 20% of perfect balance
+    }
     struct Rng { int64_t a, b; };
     std::vector<Rng> rngs(3 * (size_t)nm, Rng{0, 0});
     for (uint32_t i = 0; i < nm; ++i) {
@@ -487,7 +510,9 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
             }
         }
         int64_t clo = std::max(lo, -d), chi = std::max(clo, std::min(hi, d + 1));
-        if (sharded) {  // this rank's contiguous slice of the exponent window
+        if (sharded && by_job) {
+            if (owner[i] != (int)rank) chi = clo;  // another rank's MSM
+        } else if (sharded) {  // this rank's contiguous slice of the exponent window
             const int64_t span = chi - clo;
             const int64_t a = clo + span * (int64_t)rank / (int64_t)world, b = clo + span * (int64_t)(rank + 1) / (int64_t)world;
             clo = a;
@@ -507,10 +532,26 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
         jobs[i].scalar_off = (uint32_t)((pm[i].scal - sbase) + (slice_lo[i] - pm[i].lo));
     G1Affine* d_aff = ar.get<G1Affine>(nm);
     uint8_t* d_comp = ar.get<uint8_t>((size_t)nm * 48);
-    for (uint32_t first = 0; first < nm; first += MSM_MAX_JOBS) {
-        const uint32_t cnt = std::min<uint32_t>(MSM_MAX_JOBS, nm - first);
-        std::vector<MsmJob> part(jobs.begin() + first, jobs.begin() + first + cnt);
-        msm_run(cx, srs->points, srs->tables, (const uint32_t*)sbase, part, d_aff + first, d_comp + (size_t)first * 48);
+    if (sharded && by_job) {
+        // only this rank's MSMs enter the pipeline; the others contribute the identity
+        SONIC_CUDA(cudaMemsetAsync(d_aff, 0, (size_t)nm * sizeof(G1Affine), st));
+        std::vector<uint32_t> mine;
+        for (uint32_t i = 0; i < nm; ++i) if (owner[i] == (int)rank) mine.push_back(i);
+        G1Affine* d_mine = ar.get<G1Affine>(mine.size() ? mine.size() : 1);
+        for (size_t first = 0; first < mine.size(); first += MSM_MAX_JOBS) {
+            const size_t cnt = std::min<size_t>(MSM_MAX_JOBS, mine.size() - first);
+            std::vector<MsmJob> part;
+            for (size_t k = 0; k < cnt; ++k) part.push_back(jobs[mine[first + k]]);
+            msm_run(cx, srs->points, srs->tables, (const uint32_t*)sbase, part, d_mine + first, nullptr);
+        }
+        for (size_t k = 0; k < mine.size(); ++k)
+            SONIC_CUDA(cudaMemcpyAsync(d_aff + mine[k], d_mine + k, sizeof(G1Affine), cudaMemcpyDeviceToDevice, st));
+    } else {
+        for (uint32_t first = 0; first < nm; first += MSM_MAX_JOBS) {
+            const uint32_t cnt = std::min<uint32_t>(MSM_MAX_JOBS, nm - first);
+            std::vector<MsmJob> part(jobs.begin() + first, jobs.begin() + first + cnt);
+            msm_run(cx, srs->points, srs->tables, (const uint32_t*)sbase, part, d_aff + first, d_comp + (size_t)first * 48);
+        }
     }
 
     // ---- results to the host ---------------------------------------------------------------------

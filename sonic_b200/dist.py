@@ -21,6 +21,22 @@ def slice_bounds(lo: int, hi: int, rank: int, world: int) -> Tuple[int, int]:
     return lo + span * rank // world, lo + span * (rank + 1) // world
 
 
+def deal_jobs(lengths: Sequence[int], world: int):
+    """How prove_run (csrc/prove.cu) deals whole MSMs to ranks: longest first, each to the least
+    loaded rank.  Returns (owner per job, by_job) where by_job says whether that assignment is
+    within 20% of perfect balance; otherwise every MSM is sliced with `slice_bounds` instead."""
+    order = sorted(range(len(lengths)), key=lambda i: -lengths[i])  # stable: ties keep record order
+    load = [0] * world
+    owner = [-1] * len(lengths)
+    for i in order:
+        r = min(range(world), key=lambda k: load[k])
+        owner[i] = r
+        load[r] += lengths[i]
+    total = sum(lengths)
+    by_job = len(lengths) >= world and max(load) * world <= total + total // 5
+    return owner, by_job
+
+
 def all_gather_bytes(blob: bytes, group=None) -> List[bytes]:
     """All-gather of one fixed-size byte blob per rank; returns the blobs in rank order."""
     world = dist.get_world_size(group)

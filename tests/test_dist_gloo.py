@@ -93,3 +93,21 @@ def test_plan_matches_prove_dense():
     g48 = [bls.g1_compress(S.fold_msm(srs, m)) for m in msms]
     want, _ = S.prove_dense(srs, assignment, circuit, rnd)
     assert S.assemble_proof_bytes(2, g48, fvals) == S.encode_proof(want)
+
+
+def test_job_dealing_is_balanced_and_total():
+    sys.path.insert(0, ROOT)
+    from sonic_b200 import dist as sdist
+
+    n, Q = 1 << 16, 8
+    r, t, s_, c = 3 * n + 5, 7 * n + 9, 3 * n + 1, 2 * n + Q + 1
+    lengths = [r, t, r - 1, r - 1, t - 1] + [s_, s_ - 1] * Q + [s_ - 1, c - 1] * Q + [c - 1, c]
+    assert len(lengths) == 4 * Q + 7
+    for world in (2, 4, 8):
+        owner, by_job = sdist.deal_jobs(lengths, world)
+        assert by_job and sorted(set(owner)) == list(range(world))
+        load = [sum(l for l, o in zip(lengths, owner) if o == k) for k in range(world)]
+        assert max(load) * world <= sum(lengths) * 1.2
+    # a single huge MSM cannot be dealt: fall back to slicing
+    assert sdist.deal_jobs([1000, 10, 10], 2)[1] is False
+    assert sdist.deal_jobs([5], 2)[1] is False

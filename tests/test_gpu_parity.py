@@ -228,3 +228,29 @@ def test_hsc_prove_vs_oracle(gpu):
         assert got.hscW == [(a, C(b), C(c)) for a, b, c in want.hscW]
         assert (got.hscQv, got.hscC, got.hscU, got.hscV) == (C(want.hscQv), C(want.hscC), u, v)
         assert S.hscVerify_trapdoor(o, sXY, yzs, want)
+
+
+def test_srs_save_load_roundtrip(gpu, tmp_path):
+    """a saved SRS loads back to the same resident arrays (same commitments,
+    same proof), with and without precomputed levels."""
+    rng = random.Random(20)
+    circuit, assignment = example2(12)
+    gc, ga = to_gpu_types(gpu, circuit, assignment)
+    rnd = [rng.randrange(1, R) for _ in range(S.rnd_count(5))]
+    try:
+        for pre in (-1, 0):
+            gpu.set_option("precompute", pre)
+            x, alpha = rng.randrange(1, R), rng.randrange(1, R)
+            g = gpu.SRS.new(33, x, alpha)
+            path = str(tmp_path / f"srs_{pre}.bin")
+            g.save(path)
+            g2 = gpu.SRS.load(path)
+            assert g2.srsD == 33
+            assert g2.gPositiveAlphaX == g.gPositiveAlphaX and g2.gNegativeX == g.gNegativeX
+            assert gpu.prove_bytes(g2, ga, gc, rnd) == gpu.prove_bytes(g, ga, gc, rnd)
+    finally:
+        gpu.set_option("precompute", -1)
+    with open(str(tmp_path / "bad.bin"), "wb") as fh:
+        fh.write(b"not an srs")
+    with pytest.raises(gpu.SonicError):
+        gpu.SRS.load(str(tmp_path / "bad.bin"))

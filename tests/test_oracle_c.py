@@ -32,6 +32,8 @@ def test_c_srs_and_msm_match_python_oracle():
     want = bls.g1_msm_naive([pt(0, k) for k in range(-d, d + 1)], sc)
     for threads in (1, 3):
         assert cref.msm_naive(raw[:96 * stride], fb(sc), stride, threads) == bls.g1_compress(want)
+    for c in (4, 7, 13):
+        assert cref.msm_pippenger(raw[:96 * stride], fb(sc), stride, c, threads=3) == bls.g1_compress(want)
     with pytest.raises(ZeroDivisionError):
         cref.srs_new(4, 0, 1)
 
