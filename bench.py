@@ -241,24 +241,32 @@ def main() -> None:
     written = ctypes.c_uint64(0)
     terms = msm_terms_per_proof(n, Q)
 
-    def gather_and_combine(blob: bytes) -> bytes:
-        blobs = sdist.all_gather_bytes(blob)
-        proof = ctypes.create_string_buffer(proof_size)
-        capi.check(L.sonic_prove_combine(Q, world, b"".join(blobs), proof, proof_size, ctypes.byref(written)))
-        return proof.raw
+    nm = 4 * Q + 7
+    proof_buf = ctypes.create_string_buffer(proof_size)
+    if world > 1:
+        # the exchange stays on the device: partial sums -> NCCL all-gather over NVLink -> fold
+        part_t = torch.empty(nm * 96, dtype=torch.uint8, device="cuda")
+        gath_t = torch.empty(world * nm * 96, dtype=torch.uint8, device="cuda")
+
+    def exchange_and_combine() -> bytes:
+        dist.all_gather_into_tensor(gath_t, part_t)
+        torch.cuda.current_stream().synchronize()
+        capi.check(L.sonic_prove_combine_device(Q, world, gath_t.data_ptr(), out, proof_buf, proof_size, ctypes.byref(written)))
+        return proof_buf.raw
 
     def step_resident() -> bytes:
-        capi.check(L.sonic_prove_shard_device(srs._h, ch, d_in, d_rnd, hrnd, rank, world, out, len(out), ctypes.byref(written)))
         if world == 1:
+            capi.check(L.sonic_prove_device(srs._h, ch, d_in, d_rnd, hrnd, out, len(out), ctypes.byref(written)))
             return out.raw[:proof_size]
-        return gather_and_combine(out.raw[:blob_size])
+        capi.check(L.sonic_prove_shard_sink(srs._h, ch, d_in, 1, d_rnd, hrnd, rank, world, out, len(out), ctypes.byref(written), part_t.data_ptr()))
+        return exchange_and_combine()
 
     def step_e2e() -> bytes:
         if world == 1:
             capi.check(L.sonic_prove(srs._h, ch, hin, hin + n * 32, hin + 2 * n * 32, hrnd, out, len(out), ctypes.byref(written)))
             return out.raw[:proof_size]
-        capi.check(L.sonic_prove_shard(srs._h, ch, hin, hin + n * 32, hin + 2 * n * 32, hrnd, rank, world, out, len(out), ctypes.byref(written)))
-        return gather_and_combine(out.raw[:blob_size])
+        capi.check(L.sonic_prove_shard_sink(srs._h, ch, hin, 0, None, hrnd, rank, world, out, len(out), ctypes.byref(written), part_t.data_ptr()))
+        return exchange_and_combine()
 
     def timed(step, steps):
         barrier()
@@ -337,13 +345,18 @@ def main() -> None:
     sweep = []
     if not args.no_sweep:
         top = max(16, min(args.sweep_max, 24))
+        # sizes up to 2^20 run against an SRS small enough for the precomputed window tables
+        # (d = 2^19: 3.2 GB of tables); larger sizes against a d = 2^(top-1) SRS without tables
+        small_d = 1 << 19
+        small = srs if small_d <= d else sb.SRS.new(small_d, x, alpha)
         dd = 1 << (top - 1)
-        big = srs if dd <= d else sb.SRS.new(dd, x, alpha)
+        big = small if dd <= small_d else sb.SRS.new(dd, x, alpha)
         for logn in range(16, top + 1, 2):
             N = 1 << logn
             for kind in ("uniform", "skewed"):
                 if kind == "skewed" and logn not in (20, top):
                     continue
+                use = small if N <= 2 * small_d else big
                 sc = synth.fr_bytes_fast(logn, N) if kind == "uniform" else synth.skewed_fr_bytes(logn, N)
                 lo, hi = sdist.slice_bounds(-(N // 2), N // 2, rank, world)
                 part = np.ascontiguousarray(sc[lo + N // 2:hi + N // 2])
@@ -354,9 +367,9 @@ def main() -> None:
 
                 def one():
                     if world == 1:
-                        capi.check(L.sonic_msm_g1_device(big._h, 0, lo, hi - lo, dsc, o48))
+                        capi.check(L.sonic_msm_g1_device(use._h, 0, lo, hi - lo, dsc, o48))
                         return o48.raw[:48]
-                    capi.check(L.sonic_msm_g1_device_partial(big._h, 0, lo, hi - lo, dsc, o48))
+                    capi.check(L.sonic_msm_g1_device_partial(use._h, 0, lo, hi - lo, dsc, o48))
                     parts = sdist.all_gather_bytes(o48.raw)
                     return sb.g1_sum(parts)
                 for _ in range(2):
@@ -371,7 +384,7 @@ def main() -> None:
                 barrier()
                 sweep.append({"log2_n": logn, "scalars": kind, "ms": ms, "mpoints_per_s": N / (ms * 1e-3) / 1e6,
                               "frac_of_imad_peak": N * CANON_LMAC_PER_POINT / (ms * 1e-3) / imad_peak,
-                              "window_bits": sb.last_timing_ms("msm.window_bits")})
+                              "window_bits": sb.last_timing_ms("msm.window_bits"), "precomputed_tables": bool(sb.last_timing_ms("msm.precomputed"))})
                 capi.check(L.sonic_dev_free(dsc))
 
     # ---- BASELINE config 5: SRS.new at d = 2^22, then a batch of 64 independent proofs at n = 2^14 -------
@@ -441,7 +454,7 @@ def main() -> None:
             "config": {"workload": "prove() on a synthetic circuit, n=2^%d mult constraints, Q=%d, d=7n=%d, SRS resident in HBM "
                                    "(BASELINE.json config 4); %d MSM terms in %d MSMs per proof" % (args.log_n, Q, d, terms, 4 * Q + 7),
                        "n": n, "Q": Q, "d": d, "msm_terms_per_proof": terms, "ntt_len": 1 << (7 * n + 9 - 1).bit_length(),
-                       "parallelism": "1 GPU" if world == 1 else "%d GPUs: every MSM cut into %d contiguous slices, 1 NCCL all-gather of %d B per rank per proof" % (world, world, blob_size),
+                       "parallelism": "1 GPU" if world == 1 else "%d GPUs: the 4Q+7 MSMs of a proof dealt to the %d ranks (sliced if they cannot balance), 1 NCCL all-gather of %d B per rank per proof (device buffers)" % (world, world, (4 * Q + 7) * 96),
                        "l2": "inputs larger than L2: the resident SRS is %.0f MB and is gathered at random every step" % ((4 * d + 2) * 96 / 1e6),
                        "srs_new_ms": {"wall": srs_new_wall_ms, "device": srs_new_dev_ms, "points": 4 * d + 1}},
             "clocks": clocks,

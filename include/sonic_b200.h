@@ -146,6 +146,19 @@ int sonic_prove_shard(const sonic_srs* srs, const sonic_circuit* circuit, const 
 int sonic_prove_combine(uint64_t Q, uint32_t world, const uint8_t* blobs, uint8_t* proof_out,
                         uint64_t cap, uint64_t* written);
 
+/* Exchange on the device: sonic_prove_shard_sink additionally leaves the 4Q+7 raw partial sums
+ * (96 B each) at `d_partials_out`, a device buffer of the caller -- typically the input of an NCCL
+ * all-gather -- and sonic_prove_combine_device folds the gathered device buffer ([world][4Q+7] x 96 B)
+ * directly; the field values are the same on every rank and come from the rank's own blob.
+ * `assignment`: aL | aR | aO contiguous (3n Fr), host or device as flagged; `d_rnd_or_null`: the
+ * draws in device memory if already there. */
+int sonic_prove_shard_sink(const sonic_srs* srs, const sonic_circuit* circuit, const void* assignment,
+                           int assignment_on_device, const void* d_rnd_or_null, const uint8_t* rnd_host,
+                           uint32_t rank, uint32_t world, uint8_t* blob_out, uint64_t cap,
+                           uint64_t* written, void* d_partials_out);
+int sonic_prove_combine_device(uint64_t Q, uint32_t world, const void* d_gathered, const uint8_t* own_blob,
+                               uint8_t* proof_out, uint64_t cap, uint64_t* written);
+
 /* Same proof, with the assignment (aL | aR | aO, 3n Fr, canonical) and the draws already
  * resident in device memory; `rnd_host` is the host copy of the draws (zero checks, hscU/hscV).
  * Used by bench.py to time the path without the host->device copy of the inputs. */

@@ -57,6 +57,8 @@ SYMBOLS = {
     "sonic_prove": (c_int, [c_void_p, c_void_p, _u8p, _u8p, _u8p, _u8p, _u8p, c_uint64, POINTER(c_uint64)]),
     "sonic_shard_blob_size": (c_uint64, [c_uint64]),
     "sonic_prove_shard": (c_int, [c_void_p, c_void_p, _u8p, _u8p, _u8p, _u8p, ctypes.c_uint32, ctypes.c_uint32, _u8p, c_uint64, POINTER(c_uint64)]),
+    "sonic_prove_shard_sink": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, _u8p, ctypes.c_uint32, ctypes.c_uint32, _u8p, c_uint64, POINTER(c_uint64), c_void_p]),
+    "sonic_prove_combine_device": (c_int, [c_uint64, ctypes.c_uint32, c_void_p, _u8p, _u8p, c_uint64, POINTER(c_uint64)]),
     "sonic_prove_combine": (c_int, [c_uint64, ctypes.c_uint32, _u8p, _u8p, c_uint64, POINTER(c_uint64)]),
     "sonic_prove_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, _u8p, _u8p, c_uint64, POINTER(c_uint64)]),
     "sonic_prove_shard_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, _u8p, ctypes.c_uint32, ctypes.c_uint32, _u8p, c_uint64, POINTER(c_uint64)]),

@@ -273,6 +273,7 @@ int sonic_init(const int* devices, int ndev) {
         cx.sm_count = prop.multiProcessorCount;
         SONIC_CUDA(cudaStreamCreateWithFlags(&cx.stream, cudaStreamNonBlocking));
         for (auto& e : cx.ev) SONIC_CUDA(cudaEventCreate(&e));
+        if (const char* e = getenv("SONIC_ACC_BLOCKS")) { int v = atoi(e); if (v >= 2 && v <= 5) cx.opt_acc_blocks = v; }
         cx.ready = true;
     } catch (const CudaError& e) {
         cudaGetLastError();
@@ -678,6 +679,37 @@ int sonic_prove_shard(const sonic_srs* srs, const sonic_circuit* circuit, const 
         tm.stop();
         return rc;
     });
+}
+
+int sonic_prove_shard_sink(const sonic_srs* srs, const sonic_circuit* circuit, const void* assignment, int assignment_on_device,
+                           const void* d_rnd_or_null, const uint8_t* rnd_host, uint32_t rank, uint32_t world,
+                           uint8_t* blob_out, uint64_t cap, uint64_t* written, void* d_partials_out) {
+    if (!srs || !circuit || !assignment || !rnd_host || !blob_out) return fail(SONIC_ERR_INVALID_ARG, "null argument");
+    if (world < 2 || rank >= world || world > 64) return fail(SONIC_ERR_INVALID_ARG, "need 2 <= world <= 64 and rank < world");
+    const uint64_t n = circuit_n(circuit), Q = circuit_Q(circuit);
+    if (srs->d < 7 * n)
+        return fail(SONIC_ERR_D_TOO_SMALL, "Parameter d is not large enough: %" PRIu64 " should be greater than %" PRIu64, srs->d, 7 * n);
+    for (uint64_t i = 4; i < 2 * Q + 8; ++i)
+        if (fr_bytes_zero(rnd_host + 32 * i)) return fail(SONIC_ERR_DIV_BY_ZERO, "prove: recip 0 (challenge %" PRIu64 " is zero)", i);
+    return guarded([&](Ctx& cx) {
+        Timer tm(cx);
+        const Fr* d_in = (const Fr*)assignment;
+        if (!assignment_on_device) {
+            Fr* up = cx.arena.get<Fr>(3 * n);
+            SONIC_CUDA(cudaMemcpyAsync(up, assignment, 3 * n * 32, cudaMemcpyHostToDevice, cx.stream));
+            d_in = up;
+        }
+        const Fr* d_rnd = d_rnd_or_null ? (const Fr*)d_rnd_or_null : upload_fr(cx, rnd_host, 2 * Q + 8);
+        int rc = prove_run(cx, srs, circuit, d_in, d_rnd, (uint32_t)Q, true, rank, world, blob_out, cap, written, d_partials_out);
+        tm.stop();
+        return rc;
+    });
+}
+
+int sonic_prove_combine_device(uint64_t Q, uint32_t world, const void* d_gathered, const uint8_t* own_blob,
+                               uint8_t* proof_out, uint64_t cap, uint64_t* written) {
+    if (!d_gathered || !own_blob || !proof_out || world < 1 || world > 64 || Q == 0 || Q >= (1u << 16)) return fail(SONIC_ERR_INVALID_ARG, "bad argument");
+    return guarded([&](Ctx& cx) { return prove_combine(cx, (uint32_t)Q, true, world, own_blob, proof_out, cap, written, d_gathered); });
 }
 
 int sonic_prove_combine(uint64_t Q, uint32_t world, const uint8_t* blobs, uint8_t* proof_out, uint64_t cap, uint64_t* written) {

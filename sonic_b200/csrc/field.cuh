@@ -105,6 +105,7 @@ struct Chain {
 // --------------------------------------------------------------------------------------
 template <class P>
 struct alignas(16) Fp {
+    using Params = P;
     static constexpr int N = P::N;
     uint32_t l[N];
 
@@ -239,19 +240,22 @@ SONIC_HD Fp<P> fp_mul_unrolled(const Fp<P>& a, const Fp<P>& b) {
 // where they started), the multiplier limbs rotated through registers.  Same IMAD count, one
 // sixth of the code: a point addition then fits the instruction cache, which the fully
 // unrolled form (67 KB per mixed addition) does not.
-template <class P>
+template <class P, int ROWS_PER_ITER = 2>
 SONIC_HD Fp<P> fp_mul_rolled(const Fp<P>& a, const Fp<P>& b) {
     constexpr int N = P::N;
-    static_assert(N % 2 == 0, "even limb count");
+    static_assert(N % 2 == 0 && ROWS_PER_ITER % 2 == 0 && N % ROWS_PER_ITER == 0, "row grouping");
     uint32_t ev[N], od[N], bb[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) { ev[k] = 0; od[k] = 0; bb[k] = b.l[k]; }
 #pragma unroll 1
-    for (int i = 0; i < N; i += 2) {
-        mont_row_next<P>(ev, od, a.l, bb[0]);  // even-aligned now in od
-        mont_row_next<P>(od, ev, a.l, bb[1]);  // and back in ev
+    for (int i = 0; i < N; i += ROWS_PER_ITER) {
 #pragma unroll
-        for (int k = 0; k < N - 2; ++k) bb[k] = bb[k + 2];
+        for (int r = 0; r < ROWS_PER_ITER; r += 2) {
+            mont_row_next<P>(ev, od, a.l, bb[r]);      // even-aligned now in od
+            mont_row_next<P>(od, ev, a.l, bb[r + 1]);  // and back in ev
+        }
+#pragma unroll
+        for (int k = 0; k < N - ROWS_PER_ITER; ++k) bb[k] = bb[k + ROWS_PER_ITER];
     }
     Fp<P> r;
     r.l[0] = Chain::add_cc(ev[1], od[0]);
@@ -497,7 +501,9 @@ SONIC_HD Fp<P> fp_mul_sub2(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const
 template <class P>
 SONIC_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
 #if SONIC_MUL_VARIANT == 1
-    return fp_mul_rolled(a, b);
+    return fp_mul_rolled<P, (P::N % 4 == 0 ? 4 : 2)>(a, b);
+#elif SONIC_MUL_VARIANT == 3
+    return fp_mul_rolled<P, P::N / 2>(a, b);
 #elif SONIC_MUL_VARIANT == 2
     return fp_mul_karatsuba(a, b);
 #else

@@ -101,9 +101,10 @@ uint64_t circuit_Q(const sonic_circuit* c);
 // world == 1: `out` receives the proof.  world > 1: this rank's slice of every MSM; `out` receives a
 // shard blob (raw partial sums + field values) for prove_combine.
 int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr* d_in, const Fr* d_rnd,
-              uint32_t M, bool has_main, uint32_t rank, uint32_t world, uint8_t* out, uint64_t cap, uint64_t* written);
+              uint32_t M, bool has_main, uint32_t rank, uint32_t world, uint8_t* out, uint64_t cap, uint64_t* written,
+              void* d_partials_out = nullptr);
 int prove_combine(Ctx& cx, uint32_t M, bool has_main, uint32_t world, const uint8_t* blobs, uint8_t* out,
-                  uint64_t cap, uint64_t* written);
+                  uint64_t cap, uint64_t* written, const void* d_gathered = nullptr);
 }  // namespace sonic
 
 // Resident SRS.  Device layout: one array of affine points indexed by exponent,

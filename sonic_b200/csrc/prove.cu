@@ -278,18 +278,25 @@ __global__ void k_fold_partials(const Fq* __restrict__ raw, uint32_t nm, uint32_
 // of every MSM; its output is then a "shard blob" = nm raw partial sums (96 B) followed by the
 // nF field values (32 B) in record order.  prove_combine folds the gathered blobs.
 int prove_combine(Ctx& cx, uint32_t M, bool has_main, uint32_t world, const uint8_t* blobs, uint8_t* out,
-                  uint64_t cap, uint64_t* written) {
+                  uint64_t cap, uint64_t* written, const void* d_gathered) {
     const uint32_t nm = has_main ? 4 * M + 7 : 4 * M + 2;
     const uint32_t nF = has_main ? 2 * M + 5 : 2 * M + 2;
     const uint64_t blob = (uint64_t)nm * 96 + (uint64_t)nF * 32;
     const uint64_t need = (uint64_t)nm * 48 + (uint64_t)nF * 32;
     if (written) *written = need;
     if (cap < need) return fail(SONIC_ERR_BUFFER_TOO_SMALL, "proof needs %llu bytes", (unsigned long long)need);
-    Fq* d_raw = cx.arena.get<Fq>(2 * (size_t)nm * world);
-    for (uint32_t r = 0; r < world; ++r)
+    // d_gathered: the partial sums of all ranks already in device memory, [world][nm] x 96 B (the
+    // output of the all-gather); then `blobs` is this rank's own blob and only supplies the field values
+    const Fq* d_raw_c = (const Fq*)d_gathered;
+    Fq* d_raw = nullptr;
+    if (!d_gathered) {
+        d_raw = cx.arena.get<Fq>(2 * (size_t)nm * world);
+        d_raw_c = d_raw;
+    }
+    for (uint32_t r = 0; r < world && !d_gathered; ++r)
         SONIC_CUDA(cudaMemcpyAsync(d_raw + 2 * (size_t)r * nm, blobs + r * blob, (size_t)nm * 96, cudaMemcpyHostToDevice, cx.stream));
     uint8_t* d_out = cx.arena.get<uint8_t>((size_t)nm * 48);
-    SONIC_LAUNCH(k_fold_partials, div_up(nm, 32), 32, 0, d_raw, nm, world, d_out);
+    SONIC_LAUNCH(k_fold_partials, div_up(nm, 32), 32, 0, d_raw_c, nm, world, d_out);
     std::vector<uint8_t> g48((size_t)nm * 48);
     SONIC_CUDA(cudaMemcpyAsync(g48.data(), d_out, g48.size(), cudaMemcpyDeviceToHost, cx.stream));
     SONIC_CUDA(cudaStreamSynchronize(cx.stream));
@@ -298,7 +305,8 @@ int prove_combine(Ctx& cx, uint32_t M, bool has_main, uint32_t world, const uint
 }
 
 int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr* d_in, const Fr* d_rnd,
-              uint32_t M, bool has_main, uint32_t rank, uint32_t world, uint8_t* out, uint64_t cap, uint64_t* written) {
+              uint32_t M, bool has_main, uint32_t rank, uint32_t world, uint8_t* out, uint64_t cap, uint64_t* written,
+              void* d_partials_out) {
     const uint32_t n = (uint32_t)circ->n, Q = (uint32_t)circ->Q;
     const int64_t d = (int64_t)srs->d;
     const uint32_t nG = has_main ? 4 * M + 7 : 4 * M + 2;
@@ -564,6 +572,8 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
         Fq* d_raw = ar.get<Fq>(2 * (size_t)nm);
         SONIC_LAUNCH(k_points_to_raw, div_up(nm, 64), 64, 0, d_aff, nm, d_raw);
         SONIC_CUDA(cudaMemcpyAsync(h_comp.data(), d_raw, h_comp.size(), cudaMemcpyDeviceToHost, st));
+        if (d_partials_out)  // exchange buffer of the caller (e.g. the input of an NCCL all-gather)
+            SONIC_CUDA(cudaMemcpyAsync(d_partials_out, d_raw, h_comp.size(), cudaMemcpyDeviceToDevice, st));
     } else {
         SONIC_CUDA(cudaMemcpyAsync(h_comp.data(), d_comp, h_comp.size(), cudaMemcpyDeviceToHost, st));
     }

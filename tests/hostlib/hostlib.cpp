@@ -31,9 +31,11 @@ void ht_fq_mulvar(int op, const uint32_t* a, const uint32_t* b, const uint32_t* 
     Fq x = ld<Fq>(a), y = ld<Fq>(b), z = ld<Fq>(c), w = ld<Fq>(d), r;
     switch (op) {
         case 0: r = fp_mul_unrolled(x, y); break;
-        case 1: r = fp_mul_rolled(x, y); break;
+        case 1: r = fp_mul_rolled<FqParams, 2>(x, y); break;
         case 2: r = fp_mul_karatsuba(x, y); break;
         case 3: r = fp_mul_add2(x, y, z, w); break;
+        case 5: r = fp_mul_rolled<FqParams, 4>(x, y); break;
+        case 6: r = fp_mul_rolled<FqParams, 6>(x, y); break;
         default: r = fp_mul_sub2(x, y, z, w); break;
     }
     st(out, r);

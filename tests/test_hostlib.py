@@ -135,7 +135,10 @@ def test_wide_products_and_multiplier_variants(host):
         samples = [(a, b, c, d) for a in edge for b in edge for c in (0, p - 1) for d in (1, p - 1)]
         samples += [tuple(rng.randrange(p) for _ in range(4)) for _ in range(1500)]
         for a, b, c, d in samples:
-            for op, want in ((0, a * b), (1, a * b), (2, a * b), (3, a * b + c * d), (4, a * b - c * d)):
+            ops = [(0, a * b), (1, a * b), (2, a * b), (3, a * b + c * d), (4, a * b - c * d)]
+            if n == 12:
+                ops += [(5, a * b), (6, a * b)]  # rolled, 4 and 6 rows per iteration
+            for op, want in ops:
                 out = (ctypes.c_uint32 * n)()
                 fn(op, _arr(a, n), _arr(b, n), _arr(c, n), _arr(d, n), out)
                 assert from_limbs(out) == want * Ri % p, (op, n)
