@@ -117,6 +117,14 @@ int sonic_msm_g1_device_partial(const sonic_srs* srs, int family, int64_t lo, ui
  * kept resident across proofs. */
 int sonic_circuit_load(uint64_t n, uint64_t Q, const uint8_t* wL, const uint8_t* wR,
                        const uint8_t* wO, const uint8_t* cs, sonic_circuit** out);
+/* Same circuit from sparse weights: each matrix in CSR -- rowptr (Q+1
+ * entries, rowptr[0] = 0), col (gate index, 0-based) and val (32-byte Fr per non-zero); repeated
+ * (row, col) pairs add up, as terms of a sparse polynomial do.  Replaces the Q x n dense transfer
+ * and the Q*n work of `sPoly`'s list walk (src/Sonic/Constraints.hs:48-49) by nnz. */
+int sonic_circuit_load_csr(uint64_t n, uint64_t Q, const uint64_t* rowptr_L, const uint32_t* col_L,
+                           const uint8_t* val_L, const uint64_t* rowptr_R, const uint32_t* col_R,
+                           const uint8_t* val_R, const uint64_t* rowptr_O, const uint32_t* col_O,
+                           const uint8_t* val_O, const uint8_t* cs, sonic_circuit** out);
 void sonic_circuit_free(sonic_circuit* c);
 
 /* number of Fr values `prove` draws from MonadRandom: 2Q + 8, in the order

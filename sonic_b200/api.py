@@ -56,6 +56,7 @@ class GateWeights:
 class ArithCircuit:
     weights: GateWeights
     cs: List[int]
+    sparse: bool = False  # hand the weights over in CSR form (zero weights dropped) instead of dense Q x n
     _handle: object = field(default=None, repr=False, compare=False)
 
     def handle(self) -> "_Circuit":
@@ -80,9 +81,28 @@ class _Circuit:
         if not w.wL or not w.wL[0]:
             raise SonicError(1, "Empty weights")
         self.Q, self.n = len(w.wL), len(w.wL[0])
-        flat = lambda m: _frs([v for row in m for v in row])
         h = c_void_p()
-        check(lib().sonic_circuit_load(self.n, self.Q, flat(w.wL), flat(w.wR), flat(w.wO), _frs(c.cs), ctypes.byref(h)))
+        if c.sparse:
+            import numpy as np
+
+            args, keep = [], []
+            for m in (w.wL, w.wR, w.wO):
+                rowptr, cols, vals = [0], [], []
+                for row in m:
+                    for i, v in enumerate(row):
+                        if v % R_MODULUS:
+                            cols.append(i)
+                            vals.append(v)
+                    rowptr.append(len(cols))
+                rp = np.array(rowptr, dtype=np.uint64)
+                cl = np.array(cols, dtype=np.uint32)
+                vl = np.frombuffer(_frs(vals), dtype=np.uint8).copy() if vals else np.zeros(0, dtype=np.uint8)
+                keep += [rp, cl, vl]
+                args += [rp.ctypes.data, cl.ctypes.data if len(cols) else None, vl.ctypes.data if len(cols) else None]
+            check(lib().sonic_circuit_load_csr(self.n, self.Q, *args, _frs(c.cs), ctypes.byref(h)))
+        else:
+            flat = lambda m: _frs([v for row in m for v in row])
+            check(lib().sonic_circuit_load(self.n, self.Q, flat(w.wL), flat(w.wR), flat(w.wO), _frs(c.cs), ctypes.byref(h)))
         self.h = h
 
     def __del__(self):

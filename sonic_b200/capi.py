@@ -51,6 +51,7 @@ SYMBOLS = {
     "sonic_msm_g1_device": (c_int, [c_void_p, c_int, c_int64, c_uint64, c_void_p, _u8p]),
     "sonic_msm_g1_device_partial": (c_int, [c_void_p, c_int, c_int64, c_uint64, c_void_p, _u8p]),
     "sonic_circuit_load": (c_int, [c_uint64, c_uint64, _u8p, _u8p, _u8p, _u8p, POINTER(c_void_p)]),
+    "sonic_circuit_load_csr": (c_int, [c_uint64, c_uint64] + [c_void_p] * 10 + [POINTER(c_void_p)]),
     "sonic_circuit_free": (None, [c_void_p]),
     "sonic_rnd_count": (c_uint64, [c_uint64]),
     "sonic_proof_size": (c_uint64, [c_uint64]),

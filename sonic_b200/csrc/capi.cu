@@ -622,6 +622,22 @@ int sonic_circuit_load(uint64_t n, uint64_t Q, const uint8_t* wL, const uint8_t*
     return guarded([&](Ctx& cx) { return circuit_load(cx, n, Q, wL, wR, wO, cs, out); });
 }
 
+int sonic_circuit_load_csr(uint64_t n, uint64_t Q, const uint64_t* rowptr_L, const uint32_t* col_L, const uint8_t* val_L,
+                           const uint64_t* rowptr_R, const uint32_t* col_R, const uint8_t* val_R,
+                           const uint64_t* rowptr_O, const uint32_t* col_O, const uint8_t* val_O,
+                           const uint8_t* cs, sonic_circuit** out) {
+    if (!out || !rowptr_L || !rowptr_R || !rowptr_O || !cs) return fail(SONIC_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (n == 0 || Q == 0) return fail(SONIC_ERR_INVALID_ARG, "Empty weights");
+    if (n >= (1ull << 24) || Q >= (1ull << 24)) return fail(SONIC_ERR_INVALID_ARG, "circuit too large");
+    const uint64_t* rp[3] = {rowptr_L, rowptr_R, rowptr_O};
+    const uint32_t* cl[3] = {col_L, col_R, col_O};
+    const uint8_t* vl[3] = {val_L, val_R, val_O};
+    for (int m = 0; m < 3; ++m)
+        if (rp[m][Q] && (!cl[m] || !vl[m])) return fail(SONIC_ERR_INVALID_ARG, "null CSR arrays");
+    return guarded([&](Ctx& cx) { return circuit_load_csr(cx, n, Q, rp, cl, vl, cs, out); });
+}
+
 void sonic_circuit_free(sonic_circuit* c) {
     if (!c) return;
     Ctx& cx = ctx();

@@ -93,6 +93,8 @@ namespace sonic {
 // ---- prove.cu ----------------------------------------------------------------------------
 int circuit_load(Ctx& cx, uint64_t n, uint64_t Q, const uint8_t* wL, const uint8_t* wR, const uint8_t* wO,
                  const uint8_t* cs, sonic_circuit** out);
+int circuit_load_csr(Ctx& cx, uint64_t n, uint64_t Q, const uint64_t* const row_ptr[3], const uint32_t* const col[3],
+                     const uint8_t* const val[3], const uint8_t* cs, sonic_circuit** out);
 void circuit_free(sonic_circuit* c);
 uint64_t circuit_n(const sonic_circuit* c);
 uint64_t circuit_Q(const sonic_circuit* c);

@@ -15,6 +15,7 @@
 // sampled, not derived from the transcript), so the whole proof is one call: the Fr work
 // first, then every commitment and opening of the proof as ONE batched MSM launch.
 #include <algorithm>
+#include <vector>
 
 #include "internal.h"
 
@@ -137,6 +138,63 @@ __global__ void k_build_suy_fin(const Fr* __restrict__ partial, uint32_t n, uint
     out[2 * n + 1 + q] = acc;  // exponent n + (q+1)
 }
 
+// ---- sparse (CSR / CSC) variants of the two s-builders ------------------
+struct SparseView {
+    const uint32_t* ptr;  // col_ptr (CSC) or row_ptr (CSR)
+    const uint32_t* idx;  // row (CSC) or col (CSR)
+    const Fr* val;
+};
+
+// s(X,y) from column-major weights: thread per gate i, batched over the evaluation points
+__global__ void __launch_bounds__(128) k_build_sxy_csc(SparseView L, SparseView R_, SparseView O, uint32_t n,
+                                                       const Fr* __restrict__ tabs, uint64_t tl,
+                                                       const uint32_t* __restrict__ fwd_idx, const uint32_t* __restrict__ inv_idx,
+                                                       Fr* __restrict__ out) {
+    const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 >= n) return;
+    const uint32_t b = blockIdx.y;
+    const Fr* yt = tabs + (size_t)fwd_idx[b] * tl;
+    const Fr* yi = tabs + (size_t)inv_idx[b] * tl;
+    const uint32_t i = i0 + 1;
+    Fr su = Fr::zero(), sv = Fr::zero(), sw = Fr::zero();
+    for (uint32_t k = L.ptr[i0]; k < L.ptr[i0 + 1]; ++k) su = fp_add(su, fp_mul(yt[n + 1 + L.idx[k]], L.val[k]));
+    for (uint32_t k = R_.ptr[i0]; k < R_.ptr[i0 + 1]; ++k) sv = fp_add(sv, fp_mul(yt[n + 1 + R_.idx[k]], R_.val[k]));
+    for (uint32_t k = O.ptr[i0]; k < O.ptr[i0 + 1]; ++k) sw = fp_add(sw, fp_mul(yt[n + 1 + O.idx[k]], O.val[k]));
+    sw = fp_sub(fp_sub(sw, yt[i]), yi[i]);
+    Fr* o = out + (size_t)b * (3 * (size_t)n + 1);
+    o[n - i] = su;
+    o[n + i] = sv;
+    o[2 * n + i] = sw;
+    if (i0 == 0) o[n] = Fr::zero();
+}
+
+// the Y^(n+q) coefficients of s(u,Y) from row-major weights; grid = (SUY_PARTS, Q)
+__global__ void __launch_bounds__(256) k_build_suy_dot_csr(SparseView L, SparseView R_, SparseView O, uint32_t n,
+                                                           const Fr* __restrict__ ut, const Fr* __restrict__ ui,
+                                                           Fr* __restrict__ partial) {
+    __shared__ Fr smem[8];
+    const uint32_t q = blockIdx.y;
+    const uint32_t stride = 256 * SUY_PARTS, first = blockIdx.x * 256 + threadIdx.x;
+    Fr acc = Fr::zero();
+    for (uint32_t k = L.ptr[q] + first; k < L.ptr[q + 1]; k += stride) acc = fp_add(acc, fp_mul(ui[L.idx[k] + 1], L.val[k]));
+    for (uint32_t k = R_.ptr[q] + first; k < R_.ptr[q + 1]; k += stride) acc = fp_add(acc, fp_mul(ut[R_.idx[k] + 1], R_.val[k]));
+    for (uint32_t k = O.ptr[q] + first; k < O.ptr[q + 1]; k += stride) acc = fp_add(acc, fp_mul(ut[O.idx[k] + 1 + n], O.val[k]));
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Fr y;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y.l[k] = __shfl_down_sync(0xffffffffu, acc.l[k], o);
+        acc = fp_add(acc, y);
+    }
+    if (lane == 0) smem[wid] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) acc = fp_add(acc, smem[w]);
+        partial[q * SUY_PARTS + blockIdx.x] = acc;
+    }
+}
+
 // derived scalars: pts[] = the evaluation points (Montgomery), pts[np..2np) their inverses
 // rnd_m: 2M+8 draws (Montgomery), M = number of (y_j, z_j) pairs.  Layout of pts: y, z, yz, y_1..y_M, z_1..z_M, u, v
 __global__ void k_prove_points(const Fr* __restrict__ rnd_m, uint32_t M, int has_main, Fr* __restrict__ pts) {
@@ -162,13 +220,28 @@ __global__ void __launch_bounds__(256) k_first_nonzero_job(const Fr* __restrict_
 }  // namespace sonic
 
 // resident circuit (weights in Montgomery form)
+// One sparse weight matrix on the device, both ways: by row (CSR: the Y^(n+q) dot products of
+// s(u,Y) walk rows) and by column (CSC: every X-coefficient of s(X,y) sums one column).
+struct SparseMat {
+    uint32_t* row_ptr = nullptr;  // Q+1
+    uint32_t* col = nullptr;      // nnz, gate index (0-based)
+    sonic::Fr* val = nullptr;     // nnz, Montgomery, CSR order
+    uint32_t* col_ptr = nullptr;  // n+1
+    uint32_t* row = nullptr;      // nnz, constraint index (0-based)
+    sonic::Fr* cval = nullptr;    // nnz, Montgomery, CSC order
+    uint64_t nnz = 0;
+};
+
 struct sonic_circuit {
     uint64_t n = 0, Q = 0;
-    sonic::Fr* w = nullptr;   // wL | wR | wO, each Q*n row-major, then cs (Q)
+    bool sparse = false;
+    sonic::Fr* w = nullptr;   // dense: wL | wR | wO, each Q*n row-major, then cs (Q); sparse: cs only
+    SparseMat sp[3];          // sparse: wL, wR, wO
+    char* blob = nullptr;     // one allocation behind the sparse arrays
     sonic::Fr* wL() const { return w; }
     sonic::Fr* wR() const { return w + Q * n; }
     sonic::Fr* wO() const { return w + 2 * Q * n; }
-    sonic::Fr* cs() const { return w + 3 * Q * n; }
+    sonic::Fr* cs() const { return sparse ? w : w + 3 * Q * n; }
 };
 
 namespace sonic {
@@ -207,12 +280,110 @@ int circuit_load(Ctx& cx, uint64_t n, uint64_t Q, const uint8_t* wL, const uint8
     return SONIC_OK;
 }
 
+// Sparse load: host pointers to three CSR matrices (row_ptr as u64[Q+1], col as u32[nnz], val as
+// nnz x 32 canonical bytes).  The column-major copy is built here on the host (index shuffling
+// only; every field operation stays on the device).
+int circuit_load_csr(Ctx& cx, uint64_t n, uint64_t Q, const uint64_t* const row_ptr[3], const uint32_t* const col[3],
+                     const uint8_t* const val[3], const uint8_t* cs, sonic_circuit** out) {
+    uint64_t nnz[3], total = 0;
+    for (int m = 0; m < 3; ++m) {
+        if (row_ptr[m][0] != 0) return fail(SONIC_ERR_INVALID_ARG, "CSR row_ptr must start at 0");
+        for (uint64_t q = 0; q < Q; ++q)
+            if (row_ptr[m][q + 1] < row_ptr[m][q]) return fail(SONIC_ERR_INVALID_ARG, "CSR row_ptr must be non-decreasing");
+        nnz[m] = row_ptr[m][Q];
+        if (nnz[m] >= (1ull << 31)) return fail(SONIC_ERR_INVALID_ARG, "too many non-zeros");
+        for (uint64_t k = 0; k < nnz[m]; ++k)
+            if (col[m][k] >= n) return fail(SONIC_ERR_INVALID_ARG, "CSR column index %u out of range (n = %llu)", col[m][k], (unsigned long long)n);
+        total += nnz[m];
+    }
+    // host staging: [per matrix: row_ptr u32 | col u32 | col_ptr u32 | row u32] then values (CSR order, CSC order) and cs
+    const size_t idx_words = 3 * (Q + 1) + 3 * (n + 1) + 2 * total;
+    std::vector<uint32_t> idx(idx_words);
+    std::vector<uint8_t> vals((2 * total + Q) * 32);
+    size_t iw = 0, vw = 0;
+    size_t off_rowptr[3], off_col[3], off_colptr[3], off_row[3], off_val[3], off_cval[3];
+    for (int m = 0; m < 3; ++m) {
+        off_rowptr[m] = iw;
+        for (uint64_t q = 0; q <= Q; ++q) idx[iw++] = (uint32_t)row_ptr[m][q];
+        off_col[m] = iw;
+        for (uint64_t k = 0; k < nnz[m]; ++k) idx[iw++] = col[m][k];
+        // counting sort by column -> CSC
+        off_colptr[m] = iw;
+        uint32_t* cp = &idx[iw];
+        iw += n + 1;
+        for (uint64_t k = 0; k < nnz[m]; ++k) cp[col[m][k] + 1]++;
+        for (uint64_t i = 0; i < n; ++i) cp[i + 1] += cp[i];
+        off_row[m] = iw;
+        uint32_t* rw = &idx[iw];
+        iw += nnz[m];
+        off_val[m] = vw;
+        memcpy(&vals[vw * 32], val[m], nnz[m] * 32);
+        vw += nnz[m];
+        off_cval[m] = vw;
+        std::vector<uint32_t> cursor(cp, cp + n);
+        for (uint64_t q = 0; q < Q; ++q)
+            for (uint64_t k = row_ptr[m][q]; k < row_ptr[m][q + 1]; ++k) {
+                const uint32_t dst = cursor[col[m][k]]++;
+                rw[dst] = (uint32_t)q;
+                memcpy(&vals[(vw + dst) * 32], val[m] + k * 32, 32);
+            }
+        vw += nnz[m];
+    }
+    const size_t off_cs = vw;
+    memcpy(&vals[vw * 32], cs, Q * 32);
+    vw += Q;
+
+    sonic_circuit* c = new sonic_circuit;
+    c->n = n;
+    c->Q = Q;
+    c->sparse = true;
+    const size_t idx_bytes = (idx_words * 4 + 255) & ~size_t(255);
+    const size_t val_bytes = vw * sizeof(Fr);
+    cudaError_t e = cudaMalloc((void**)&c->blob, idx_bytes + val_bytes);
+    if (e != cudaSuccess) { delete c; throw CudaError{e, "cudaMalloc(circuit)", __LINE__}; }
+    try {
+        uint32_t* d_idx = (uint32_t*)c->blob;
+        Fr* d_val = (Fr*)(c->blob + idx_bytes);
+        Fr* stage = cx.arena.get<Fr>(vw ? vw : 1);
+        SONIC_CUDA(cudaMemcpyAsync(d_idx, idx.data(), idx_words * 4, cudaMemcpyHostToDevice, cx.stream));
+        SONIC_CUDA(cudaMemcpyAsync(stage, vals.data(), vw * 32, cudaMemcpyHostToDevice, cx.stream));
+        uint32_t* bad = cx.arena.get<uint32_t>(1);
+        SONIC_CUDA(cudaMemsetAsync(bad, 0, 4, cx.stream));
+        fr_to_mont(cx, stage, d_val, vw, bad);
+        uint32_t h = 0;
+        SONIC_CUDA(cudaMemcpyAsync(&h, bad, 4, cudaMemcpyDeviceToHost, cx.stream));
+        SONIC_CUDA(cudaStreamSynchronize(cx.stream));
+        if (h) {
+            cudaFree(c->blob);
+            delete c;
+            return fail(SONIC_ERR_NONCANONICAL, "a circuit weight is not a canonical residue (>= r)");
+        }
+        for (int m = 0; m < 3; ++m) {
+            c->sp[m].row_ptr = d_idx + off_rowptr[m];
+            c->sp[m].col = d_idx + off_col[m];
+            c->sp[m].col_ptr = d_idx + off_colptr[m];
+            c->sp[m].row = d_idx + off_row[m];
+            c->sp[m].val = d_val + off_val[m];
+            c->sp[m].cval = d_val + off_cval[m];
+            c->sp[m].nnz = nnz[m];
+        }
+        c->w = d_val + off_cs;
+    } catch (...) {
+        cudaFree(c->blob);
+        delete c;
+        throw;
+    }
+    *out = c;
+    return SONIC_OK;
+}
+
 uint64_t circuit_n(const sonic_circuit* c) { return c->n; }
 uint64_t circuit_Q(const sonic_circuit* c) { return c->Q; }
 
 void circuit_free(sonic_circuit* c) {
     if (!c) return;
-    if (c->w) cudaFree(c->w);
+    if (c->sparse) { if (c->blob) cudaFree(c->blob); }
+    else if (c->w) cudaFree(c->w);
     delete c;
 }
 
@@ -367,7 +538,13 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
         }
         uint32_t* d_idx = ar.get<uint32_t>(2 * nb);
         SONIC_CUDA(cudaMemcpyAsync(d_idx, h_idx.data(), 8 * nb, cudaMemcpyHostToDevice, st));
-        SONIC_LAUNCH(k_build_sxy, dim3(div_up(n, 128), nb), 128, 0, circ->wL(), circ->wR(), circ->wO(), n, Q, tabs, tl, d_idx, d_idx + nb, sxy_m);
+        if (circ->sparse) {
+            SparseView cl{circ->sp[0].col_ptr, circ->sp[0].row, circ->sp[0].cval}, cr{circ->sp[1].col_ptr, circ->sp[1].row, circ->sp[1].cval},
+                co{circ->sp[2].col_ptr, circ->sp[2].row, circ->sp[2].cval};
+            SONIC_LAUNCH(k_build_sxy_csc, dim3(div_up(n, 128), nb), 128, 0, cl, cr, co, n, tabs, tl, d_idx, d_idx + nb, sxy_m);
+        } else {
+            SONIC_LAUNCH(k_build_sxy, dim3(div_up(n, 128), nb), 128, 0, circ->wL(), circ->wR(), circ->wO(), n, Q, tabs, tl, d_idx, d_idx + nb, sxy_m);
+        }
         fr_from_mont(cx, sxy_m, sxy_c, (size_t)nb * slen);
     }
     auto sxy = [&](uint32_t b) { Window w; w.mont = sxy_m + (size_t)b * slen; w.canon = sxy_c + (size_t)b * slen; w.lo = -(int64_t)n; w.len = slen; return w; };
@@ -381,7 +558,13 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
     SONIC_LAUNCH(k_build_suy_pm, div_up(2 * n + 1, 256), 256, 0, fwd(PT_U), n, Q, suy.mont);
     {
         Fr* part = ar.get<Fr>((size_t)Q * SUY_PARTS);
-        SONIC_LAUNCH(k_build_suy_dot, dim3(SUY_PARTS, Q), 256, 0, circ->wL(), circ->wR(), circ->wO(), n, fwd(PT_U), inv(PT_U), part);
+        if (circ->sparse) {
+            SparseView rl{circ->sp[0].row_ptr, circ->sp[0].col, circ->sp[0].val}, rr{circ->sp[1].row_ptr, circ->sp[1].col, circ->sp[1].val},
+                ro{circ->sp[2].row_ptr, circ->sp[2].col, circ->sp[2].val};
+            SONIC_LAUNCH(k_build_suy_dot_csr, dim3(SUY_PARTS, Q), 256, 0, rl, rr, ro, n, fwd(PT_U), inv(PT_U), part);
+        } else {
+            SONIC_LAUNCH(k_build_suy_dot, dim3(SUY_PARTS, Q), 256, 0, circ->wL(), circ->wR(), circ->wO(), n, fwd(PT_U), inv(PT_U), part);
+        }
         SONIC_LAUNCH(k_build_suy_fin, div_up(Q, 64), 64, 0, part, n, Q, suy.mont);
     }
     fr_from_mont(cx, suy.mont, suy.canon, suy.len);

@@ -254,3 +254,34 @@ def test_srs_save_load_roundtrip(gpu, tmp_path):
         fh.write(b"not an srs")
     with pytest.raises(gpu.SonicError):
         gpu.SRS.load(str(tmp_path / "bad.bin"))
+
+
+def test_sparse_circuit_load_gives_the_same_proof(gpu):
+    """the CSR ingestion path builds the same s(X,y), s(u,Y) and therefore
+    the same proof bytes as the dense Q x n path (and as the oracle)."""
+    rng = random.Random(21)
+    cases = [example2(12)] + [rnd_circuit(rng, n=rng.randint(3, 14)) for _ in range(3)]
+    # a circuit with genuinely sparse, non-trivial weights (several non-zeros per row and column)
+    n, Q = 9, 6
+    aL = [rng.randrange(R) for _ in range(n)]
+    aR = [rng.randrange(R) for _ in range(n)]
+    aO = [a * b % R for a, b in zip(aL, aR)]
+    mk = lambda: [[rng.randrange(R) if rng.random() < 0.3 else 0 for _ in range(n)] for _ in range(Q)]
+    wL, wR, wO = mk(), mk(), mk()
+    dot = lambda v, row: sum(a * b for a, b in zip(v, row))
+    cs = [(dot(aL, wL[q]) + dot(aR, wR[q]) + dot(aO, wO[q])) % R for q in range(Q)]
+    cases.append((S.ArithCircuit(S.GateWeights(wL, wR, wO), cs), S.Assignment(aL, aR, aO)))
+    for circuit, assignment in cases:
+        n, Q = len(assignment.aL), len(circuit.weights.wL)
+        d = 7 * n + 9
+        x, alpha = rng.randrange(1, R), rng.randrange(1, R)
+        g, o = _srs_pair(gpu, d, x, alpha)
+        rnd = [rng.randrange(1, R) for _ in range(S.rnd_count(Q))]
+        w = circuit.weights
+        dense = gpu.ArithCircuit(gpu.GateWeights(w.wL, w.wR, w.wO), circuit.cs)
+        sparse = gpu.ArithCircuit(gpu.GateWeights(w.wL, w.wR, w.wO), circuit.cs, sparse=True)
+        ga = gpu.Assignment(assignment.aL, assignment.aR, assignment.aO)
+        want, _ = S.prove_dense(o, assignment, circuit, rnd)
+        a = gpu.prove_bytes(g, ga, dense, rnd)
+        b = gpu.prove_bytes(g, ga, sparse, rnd)
+        assert a == b == S.encode_proof(want)
