@@ -185,6 +185,17 @@ int sonic_hsc_prove(const sonic_srs* srs, const sonic_circuit* circuit, uint64_t
                     const uint8_t* yzs, const uint8_t* uv, uint8_t* out, uint64_t cap,
                     uint64_t* written);
 
+/* Verifier-side G1 folding (the pairings stay on the host library).
+ * pcV (src/Sonic/CommitmentScheme.hs:51-68) for k checks (F_i, z_i, (v_i, W_i)) with caller-chosen
+ * random weights r_i reduces to ONE multi-pairing with the G1 inputs written to out48:
+ *   out[0] = A = sum r_i W_i                  to pair with hPositiveAlphaX[1]
+ *   out[1] = B = sum r_i (v_i g - z_i W_i)    to pair with hPositiveAlphaX[0]
+ *   out[2+m] = C_m = sum_{group_i = m} r_i F_i to pair with h^{x^{-d+max_m}}
+ * so that verify is:  e(A, h^{alpha x}) e(B, h^alpha) == prod_m e(C_m, hxi_m). */
+int sonic_pcv_fold(uint64_t k, const uint8_t* F48, const uint8_t* W48, const uint8_t* v32,
+                   const uint8_t* z32, const uint8_t* r32, const uint32_t* group, uint32_t ngroups,
+                   uint8_t* out48);
+
 /* ---- tuning and measurement hooks (not part of the reference surface) ---- */
 /* option names: "window_bits" (0 = automatic), "chunk" (0 = automatic),
  * "precompute" (-1 = automatic, 0 = off, c = window bits): SRS.new also stores the multiples

@@ -21,6 +21,9 @@ from .api import (  # noqa: F401
     msm_partial,
     g1_sum,
     openPoly,
+    pcv_fold,
+    prove_shard,
+    prove_combine,
     prove,
     prove_bytes,
     R_MODULUS,

@@ -352,3 +352,23 @@ def prove_combine(Q: int, blobs: Sequence[bytes]) -> bytes:
     written = c_uint64(0)
     check(lib().sonic_prove_combine(Q, len(blobs), b"".join(blobs), out, size, ctypes.byref(written)))
     return out.raw[:written.value]
+
+
+def pcv_fold(checks: Sequence[Tuple[G1Bytes, int, Tuple[int, G1Bytes], int]], weights: Sequence[int]):
+    """G1 side of a batch of `pcV` checks (src/Sonic/CommitmentScheme.hs:51-68): `checks` holds
+    (F, z, (v, W), group) with `group` numbering the distinct `max` values; returns (A, B, [C_m])
+    such that all checks hold iff e(A, h^{alpha x}) e(B, h^alpha) == prod_m e(C_m, h^{x^{-d+max_m}})
+    (up to the soundness error of the random `weights`).  The pairings stay on the host."""
+    import numpy as np
+
+    capi.init()
+    k = len(checks)
+    ng = max(c[3] for c in checks) + 1
+    F = b"".join(c[0] for c in checks)
+    W = b"".join(c[2][1] for c in checks)
+    grp = np.array([c[3] for c in checks], dtype=np.uint32)
+    out = ctypes.create_string_buffer(48 * (2 + ng))
+    check(lib().sonic_pcv_fold(k, F, W, _frs([c[2][0] for c in checks]), _frs([c[1] for c in checks]), _frs(weights),
+                               grp.ctypes.data, ng, out))
+    raw = out.raw
+    return raw[0:48], raw[48:96], [raw[96 + 48 * m:144 + 48 * m] for m in range(ng)]

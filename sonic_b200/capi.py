@@ -64,6 +64,7 @@ SYMBOLS = {
     "sonic_prove_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, _u8p, _u8p, c_uint64, POINTER(c_uint64)]),
     "sonic_prove_shard_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, _u8p, ctypes.c_uint32, ctypes.c_uint32, _u8p, c_uint64, POINTER(c_uint64)]),
     "sonic_hsc_prove": (c_int, [c_void_p, c_void_p, c_uint64, _u8p, _u8p, _u8p, c_uint64, POINTER(c_uint64)]),
+    "sonic_pcv_fold": (c_int, [c_uint64, _u8p, _u8p, _u8p, _u8p, _u8p, c_void_p, ctypes.c_uint32, _u8p]),
     "sonic_set_option": (c_int, [c_char_p, c_int64]),
     "sonic_last_timing_ms": (c_double, [c_char_p]),
     "sonic_launch_count": (c_uint64, []),

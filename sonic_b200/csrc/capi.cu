@@ -778,6 +778,18 @@ int sonic_hsc_prove(const sonic_srs* srs, const sonic_circuit* circuit, uint64_t
     });
 }
 
+int sonic_pcv_fold(uint64_t k, const uint8_t* F48, const uint8_t* W48, const uint8_t* v32, const uint8_t* z32,
+                   const uint8_t* r32, const uint32_t* group, uint32_t ngroups, uint8_t* out48) {
+    if (!F48 || !W48 || !v32 || !z32 || !r32 || !group || !out48 || k == 0 || k > (1u << 16) || ngroups == 0 || ngroups > 64)
+        return fail(SONIC_ERR_INVALID_ARG, "bad argument");
+    for (uint64_t i = 0; i < k; ++i) {
+        if (group[i] >= ngroups) return fail(SONIC_ERR_INVALID_ARG, "group index out of range");
+        if (!fr_bytes_canonical(v32 + 32 * i) || !fr_bytes_canonical(z32 + 32 * i) || !fr_bytes_canonical(r32 + 32 * i))
+            return fail(SONIC_ERR_NONCANONICAL, "an Fr encoding is not a canonical residue (>= r)");
+    }
+    return guarded([&](Ctx& cx) { return pcv_fold(cx, (uint32_t)k, F48, W48, v32, z32, r32, group, ngroups, out48); });
+}
+
 int sonic_set_option(const char* name, int64_t value) {
     if (!name) return fail(SONIC_ERR_INVALID_ARG, "null option name");
     Ctx& cx = ctx();
@@ -791,6 +803,15 @@ int sonic_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "precompute_budget_mb")) {
         if (value < 0) return fail(SONIC_ERR_INVALID_ARG, "budget must be >= 0");
         cx.opt_precompute_budget = (uint64_t)value << 20;
+    } else if (!strcmp(name, "reduce_mode")) {
+        if (value < 0 || value > 1) return fail(SONIC_ERR_INVALID_ARG, "reduce_mode must be 0 or 1");
+        cx.opt_reduce_mode = (int)value;
+    } else if (!strcmp(name, "reduce_k")) {
+        if (value < 1 || value > 256) return fail(SONIC_ERR_INVALID_ARG, "reduce_k must be in [1, 256]");
+        cx.opt_reduce_k = (int)value;
+    } else if (!strcmp(name, "reduce_blocks")) {
+        if (value < 2 || value > 4) return fail(SONIC_ERR_INVALID_ARG, "reduce_blocks must be in [2, 4]");
+        cx.opt_reduce_blocks = (int)value;
     } else if (!strcmp(name, "acc_blocks")) {
         if (value < 2 || value > 5) return fail(SONIC_ERR_INVALID_ARG, "acc_blocks must be in [2, 5]");
         cx.opt_acc_blocks = (int)value;

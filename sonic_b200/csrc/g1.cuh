@@ -154,6 +154,56 @@ SONIC_HD G1XYZZ g1_mul_small(const G1XYZZ& p, uint32_t k) {
     return r;
 }
 
+// k * p for a full-width canonical scalar (double-and-add, MSB first); for the handful of
+// arbitrary-base multiplications outside the MSM (verifier-side folding)
+SONIC_HD G1XYZZ g1_mul_scalar(const G1Affine& p, const Fr& k_canonical) {
+    G1XYZZ r = G1XYZZ::inf();
+    bool started = false;
+    for (int i = Fr::N - 1; i >= 0; --i)
+        for (int b = 31; b >= 0; --b) {
+            if (started) r = g1_dbl(r);
+            if ((k_canonical.l[i] >> b) & 1) { g1_madd(r, p); started = true; }
+        }
+    return r;
+}
+
+// Inverse of g1_compress.  Returns false for a malformed encoding (flags, x >= q, x not on the curve).
+SONIC_HD bool g1_decompress(const uint8_t in[48], G1Affine& out) {
+    if (!(in[0] & 0x80)) return false;
+    if (in[0] & 0x40) {
+        uint32_t rest = in[0] & 0x3F;
+        for (int i = 1; i < 48; ++i) rest |= in[i];
+        if (rest) return false;
+        out = G1Affine::inf();
+        return true;
+    }
+    Fq xc;
+    for (int i = 0; i < 12; ++i) {
+        uint32_t w = ((uint32_t)in[4 * i] << 24) | ((uint32_t)in[4 * i + 1] << 16) | ((uint32_t)in[4 * i + 2] << 8) | in[4 * i + 3];
+        if (i == 0) w &= 0x1FFFFFFFu;
+        xc.l[11 - i] = w;
+    }
+    // x < q ?
+    uint32_t t = Chain::sub_cc(xc.l[0], FqParams::P(0));
+    (void)t;
+#pragma unroll
+    for (int i = 1; i < 12; ++i) t = Chain::subc_cc(xc.l[i], FqParams::P(i));
+    if (Chain::subc(0, 0) == 0) return false;
+    Fq x = fp_to_mont(xc);
+    Fq b;
+    for (int i = 0; i < 12; ++i) b.l[i] = FqParams::B_M(i);
+    Fq rhs = fp_add(fp_mul(fp_sqr(x), x), b);
+    uint32_t e[12];
+    for (int i = 0; i < 12; ++i) e[i] = FqParams::SQRT_EXP(i);
+    Fq y = fp_pow_limbs(rhs, e, 12);
+    if (fp_sqr(y) != rhs) return false;
+    const bool want_big = (in[0] & 0x20) != 0;
+    if (fp_canonical_gt_half(fp_from_mont(y)) != want_big) y = fp_neg(y);
+    out.x = x;
+    out.y = y;
+    return true;
+}
+
 // 48-byte compressed boundary encoding: big-endian x, flag bits
 // 0x80 compressed, 0x40 infinity, 0x20 y > (q-1)/2.  Input is canonical affine in Montgomery form.
 SONIC_HD void g1_compress(const G1Affine& a, uint8_t out[48]) {

@@ -86,6 +86,8 @@ struct sonic_circuit;
 namespace sonic {
 // ---- selftest.cu -------------------------------------------------------------------------
 int selftest_field(Ctx& cx, int which, int op, const void* a, const void* b, void* out, uint32_t n);
+int pcv_fold(Ctx& cx, uint32_t k, const uint8_t* F48, const uint8_t* W48, const uint8_t* v32, const uint8_t* z32,
+             const uint8_t* r32, const uint32_t* group, uint32_t ngroups, uint8_t* out48);
 int selftest_g1(Ctx& cx, int op, const void* a, const void* b, void* out_aff, void* out_comp, uint32_t n);
 }  // namespace sonic
 

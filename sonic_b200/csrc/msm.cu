@@ -261,9 +261,39 @@ k_msm_heavy(const uint32_t* __restrict__ offsets, uint32_t L, G1XYZZ* __restrict
     }
 }
 
-// ---- stage 6: per-window bucket reduction  sum_b (b+1) * B_b ------------------------------
+// ---- stage 6: bucket reduction  sum_b (b+1) * B_b  per bucket set, level by level ----------------
+// Items come in sets of `count` consecutive elements; a thread folds K consecutive items of one
+// set with the running-sum trick (2 additions per item) and emits
+//   out_x = sum of its x items                      (still to be weighted by the levels above)
+//   out_y = sum of its y items + 2^shift * sum_k (k + one_based) * x_k
+// where y carries what is already fully weighted.  The next level sees count/K items whose index
+// weight is worth K times more (shift += log2 K).  About 2.2 additions per bucket in total, no
+// per-thread scalar multiplication, and every level is as wide as it has items.
+__global__ void __launch_bounds__(128)
+k_msm_bucket_level(const G1XYZZ* __restrict__ in_x, const G1XYZZ* __restrict__ in_y, uint32_t count, uint32_t K,
+                   uint32_t shift, uint32_t one_based, G1XYZZ* __restrict__ out_x, G1XYZZ* __restrict__ out_y,
+                   uint32_t total_threads) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_threads) return;
+    const uint32_t per_set = count / K;
+    const uint32_t set = t / per_set, u = t - set * per_set;
+    const size_t base = (size_t)set * count + (size_t)u * K;
+    G1XYZZ run = G1XYZZ::inf(), acc = G1XYZZ::inf();
+    for (uint32_t k = K; k-- > 0;) {
+        g1_add(run, load_xyzz(in_x + base + k));
+        if (k > 0 || one_based) g1_add(acc, run);
+    }
+    for (uint32_t i = 0; i < shift; ++i) acc = g1_dbl(acc);
+    if (in_y)
+        for (uint32_t k = 0; k < K; ++k) g1_add(acc, load_xyzz(in_y + base + k));
+    store_xyzz(out_x + t, run);
+    store_xyzz(out_y + t, acc);
+}
+
+// ---- stage 6 (flat variant): per-window bucket reduction  sum_b (b+1) * B_b ------------------------------
 // grid = (blocks_per_window, windows_total); each thread owns K consecutive buckets.
-__global__ void __launch_bounds__(MSM_RED_THREADS)
+template <int MINB>
+__global__ void __launch_bounds__(MSM_RED_THREADS, MINB)
 k_msm_bucket_reduce(const G1XYZZ* __restrict__ buckets, uint32_t B, uint32_t K, G1XYZZ* __restrict__ partial) {
     __shared__ G1XYZZ smem[MSM_RED_THREADS];
     const uint32_t window = blockIdx.y;
@@ -432,9 +462,40 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const u
     SONIC_LAUNCH(k_msm_heavy, cx.sm_count * 2, MSM_RED_THREADS, 0, offsets, p.L, buckets, head, tail, heavy_count, heavy_list);
     SONIC_CUDA(cudaEventRecord(cx.ev[2], st));
 
-    G1XYZZ* partial = ar.get<G1XYZZ>((size_t)M * p.sets * p.S);
-    SONIC_LAUNCH(k_msm_bucket_reduce, dim3(p.S, (unsigned)(M * p.sets)), MSM_RED_THREADS, 0, buckets, p.B, p.K, partial);
-    SONIC_LAUNCH(k_msm_finish, M, 64, 0, partial, p.S, p.sets, p.c, d_out_aff, d_out_comp);
+    if (cx.opt_reduce_mode == 0) {
+        // flat: each thread K buckets + its offset multiple, block tree, per-job fold of the block partials
+        uint32_t K = (uint32_t)cx.opt_reduce_k;
+        if (K > p.B / MSM_RED_THREADS) K = p.B / MSM_RED_THREADS;
+        if (K < 1) K = 1;
+        const uint32_t S = div_up(p.B, (uint64_t)MSM_RED_THREADS * K);
+        G1XYZZ* partial = ar.get<G1XYZZ>((size_t)M * p.sets * S);
+        if (cx.opt_reduce_blocks >= 4) SONIC_LAUNCH(k_msm_bucket_reduce<4>, dim3(S, (unsigned)(M * p.sets)), MSM_RED_THREADS, 0, buckets, p.B, K, partial);
+        else if (cx.opt_reduce_blocks == 3) SONIC_LAUNCH(k_msm_bucket_reduce<3>, dim3(S, (unsigned)(M * p.sets)), MSM_RED_THREADS, 0, buckets, p.B, K, partial);
+        else SONIC_LAUNCH(k_msm_bucket_reduce<2>, dim3(S, (unsigned)(M * p.sets)), MSM_RED_THREADS, 0, buckets, p.B, K, partial);
+        SONIC_LAUNCH(k_msm_finish, M, 64, 0, partial, S, p.sets, p.c, d_out_aff, d_out_comp);
+    } else {
+    // level-by-level reduction of every bucket set to one point
+        const uint32_t nsets = (uint32_t)M * p.sets;
+        const G1XYZZ* lx = buckets;
+        const G1XYZZ* ly = nullptr;
+        uint32_t count = p.B, shift = 0, level = 0;
+        while (count > 1 || level == 0) {
+            uint32_t K = count >= 16 ? 16 : count;
+            if (count > 16 && count / 16 < 8) K = count / 8 >= 2 ? count / 8 : count;  // keep the last level at 8 items
+            const uint32_t threads = nsets * (count / K);
+            G1XYZZ* ox = ar.get<G1XYZZ>(threads);
+            G1XYZZ* oy = ar.get<G1XYZZ>(threads);
+            SONIC_LAUNCH(k_msm_bucket_level, div_up(threads, 128), 128, 0, lx, ly, count, K, shift, level == 0 ? 1u : 0u, ox, oy, threads);
+            lx = ox;
+            ly = oy;
+            uint32_t lg = 0;
+            while ((1u << lg) < K) ++lg;
+            shift += lg;
+            count /= K;
+            ++level;
+        }
+        SONIC_LAUNCH(k_msm_finish, M, 64, 0, ly, 1u, p.sets, p.c, d_out_aff, d_out_comp);
+    }
     SONIC_CUDA(cudaEventRecord(cx.ev[3], st));
 }
 

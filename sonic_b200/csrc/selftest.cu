@@ -70,4 +70,69 @@ int selftest_g1(Ctx& cx, int op, const void* a, const void* b, void* out_aff, vo
     return SONIC_OK;
 }
 
+// ---- verifier-side G1 folding -------------------------------------------
+// pcV (src/Sonic/CommitmentScheme.hs:51-68) checks  e(W, h^{alpha x}) e(g^v W^{-z}, h^alpha) == e(F, h^{x^{-d+max}}).
+// k such checks with random weights r_i collapse into ONE multi-pairing whose G1 inputs are
+//   A   = sum_i r_i W_i                         (against h^{alpha x})
+//   B   = sum_i r_i (v_i G - z_i W_i)           (against h^alpha)
+//   C_m = sum_{i : group_i = m} r_i F_i         (against h^{x^{-d+max_m}}, one per distinct `max`)
+// The pairings themselves stay on the host library.  One thread per check does the three scalar
+// multiplications (k is 3Q+4, a few dozen), one thread per output folds.
+__global__ void __launch_bounds__(64) k_pcv_terms(uint32_t k, const uint8_t* __restrict__ F48, const uint8_t* __restrict__ W48,
+                                                  const Fr* __restrict__ v, const Fr* __restrict__ z, const Fr* __restrict__ r,
+                                                  G1XYZZ* __restrict__ tA, G1XYZZ* __restrict__ tB, G1XYZZ* __restrict__ tC,
+                                                  uint32_t* __restrict__ bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    G1Affine F, W;
+    if (!g1_decompress(F48 + (size_t)i * 48, F) || !g1_decompress(W48 + (size_t)i * 48, W)) { atomicExch(bad, 1u); return; }
+    const Fr rm = fp_to_mont(r[i]);
+    const Fr rv = fp_from_mont(fp_mul(rm, fp_to_mont(v[i])));
+    const Fr rz = fp_from_mont(fp_mul(rm, fp_to_mont(z[i])));
+    store_xyzz(tA + i, g1_mul_scalar(W, r[i]));
+    G1XYZZ b = g1_mul_scalar(G1Affine::gen(), rv);
+    g1_add(b, g1_neg_xyzz(g1_mul_scalar(W, rz)));
+    store_xyzz(tB + i, b);
+    store_xyzz(tC + i, g1_mul_scalar(F, r[i]));
+}
+
+__global__ void k_pcv_fold(uint32_t k, const G1XYZZ* __restrict__ tA, const G1XYZZ* __restrict__ tB, const G1XYZZ* __restrict__ tC,
+                           const uint32_t* __restrict__ group, uint32_t ngroups, uint8_t* __restrict__ out48) {
+    const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;  // 0 = A, 1 = B, 2.. = C_m
+    if (o >= 2 + ngroups) return;
+    G1XYZZ acc = G1XYZZ::inf();
+    for (uint32_t i = 0; i < k; ++i) {
+        if (o == 0) g1_add(acc, load_xyzz(tA + i));
+        else if (o == 1) g1_add(acc, load_xyzz(tB + i));
+        else if (group[i] == o - 2) g1_add(acc, load_xyzz(tC + i));
+    }
+    g1_compress(g1_to_affine(acc), out48 + (size_t)o * 48);
+}
+
+int pcv_fold(Ctx& cx, uint32_t k, const uint8_t* F48, const uint8_t* W48, const uint8_t* v32, const uint8_t* z32,
+             const uint8_t* r32, const uint32_t* group, uint32_t ngroups, uint8_t* out48) {
+    uint8_t* dF = cx.arena.get<uint8_t>((size_t)k * 48);
+    uint8_t* dW = cx.arena.get<uint8_t>((size_t)k * 48);
+    Fr* dv = cx.arena.get<Fr>(3 * (size_t)k);
+    uint32_t* dg = cx.arena.get<uint32_t>(k);
+    uint32_t* bad = cx.arena.get<uint32_t>(1);
+    G1XYZZ* t = cx.arena.get<G1XYZZ>(3 * (size_t)k);
+    uint8_t* dout = cx.arena.get<uint8_t>((size_t)(2 + ngroups) * 48);
+    SONIC_CUDA(cudaMemcpyAsync(dF, F48, (size_t)k * 48, cudaMemcpyHostToDevice, cx.stream));
+    SONIC_CUDA(cudaMemcpyAsync(dW, W48, (size_t)k * 48, cudaMemcpyHostToDevice, cx.stream));
+    SONIC_CUDA(cudaMemcpyAsync(dv, v32, (size_t)k * 32, cudaMemcpyHostToDevice, cx.stream));
+    SONIC_CUDA(cudaMemcpyAsync(dv + k, z32, (size_t)k * 32, cudaMemcpyHostToDevice, cx.stream));
+    SONIC_CUDA(cudaMemcpyAsync(dv + 2 * (size_t)k, r32, (size_t)k * 32, cudaMemcpyHostToDevice, cx.stream));
+    SONIC_CUDA(cudaMemcpyAsync(dg, group, (size_t)k * 4, cudaMemcpyHostToDevice, cx.stream));
+    SONIC_CUDA(cudaMemsetAsync(bad, 0, 4, cx.stream));
+    SONIC_LAUNCH(k_pcv_terms, div_up(k, 64), 64, 0, k, dF, dW, dv, dv + k, dv + 2 * (size_t)k, t, t + k, t + 2 * (size_t)k, bad);
+    SONIC_LAUNCH(k_pcv_fold, div_up(2 + ngroups, 32), 32, 0, k, t, t + k, t + 2 * (size_t)k, dg, ngroups, dout);
+    uint32_t hbad = 0;
+    SONIC_CUDA(cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, cx.stream));
+    SONIC_CUDA(cudaMemcpyAsync(out48, dout, (size_t)(2 + ngroups) * 48, cudaMemcpyDeviceToHost, cx.stream));
+    SONIC_CUDA(cudaStreamSynchronize(cx.stream));
+    if (hbad) return fail(SONIC_ERR_INVALID_ARG, "a G1 encoding is malformed or not on the curve");
+    return SONIC_OK;
+}
+
 }  // namespace sonic

@@ -98,6 +98,15 @@ void ht_g1_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
 }
 void ht_g1_to_affine(const uint32_t* a, uint32_t* out) { sta(out, g1_to_affine(ldx(a))); }
 void ht_g1_compress(const uint32_t* aff, uint8_t* out48) { g1_compress(lda(aff), out48); }
+int ht_g1_decompress(const uint8_t* in48, uint32_t* out_aff) {
+    G1Affine a;
+    if (!g1_decompress(in48, a)) return 0;
+    sta(out_aff, a);
+    return 1;
+}
+void ht_g1_mul_scalar(const uint32_t* aff, const uint32_t* k8, uint32_t* out_xyzz) {
+    stx(out_xyzz, g1_mul_scalar(lda(aff), ld<Fr>(k8)));
+}
 void ht_g1_gen(uint32_t* out) { sta(out, G1Affine::gen()); }
 
 // signed-digit recoding of a canonical scalar: returns W digits

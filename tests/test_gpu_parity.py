@@ -285,3 +285,49 @@ def test_sparse_circuit_load_gives_the_same_proof(gpu):
         a = gpu.prove_bytes(g, ga, dense, rnd)
         b = gpu.prove_bytes(g, ga, sparse, rnd)
         assert a == b == S.encode_proof(want)
+
+
+def test_pcv_fold_batches_the_verifier_checks(gpu):
+    """the 3Q+4 pcV checks of a proof folded into one multi-pairing's G1
+    inputs.  Checked in the exponent with the trapdoor:
+        alpha*x*A + alpha*B == sum_m x^(-d+max_m) * C_m   holds for a valid proof, fails for a forged one."""
+    rng = random.Random(22)
+    circuit, assignment = example2(12)
+    n, Q, d = 2, 5, 20
+    x, alpha = rng.randrange(1, R), rng.randrange(1, R)
+    g, o = _srs_pair(gpu, d, x, alpha)
+    gc, ga = to_gpu_types(gpu, circuit, assignment)
+    rnd = [rng.randrange(1, R) for _ in range(S.rnd_count(Q))]
+    proof, orc = gpu.prove(g, ga, gc, rnd)
+    y, z, yzs = orc.rndOracleY, orc.rndOracleZ, orc.rndOracleYZs
+    ky = sum(k * S.fr_pow(y, n + 1 + q) for q, k in enumerate(circuit.cs)) % R
+    t = (proof.prA * (proof.prB + proof.prS) - ky) % R
+    h = proof.prHscProof
+    sv = S.dense_sXy(circuit.weights, h.hscV).eval(h.hscU)
+    # group 0: max = n (commitment R), group 1: max = d (everything else) -- Protocol.hs:121-124, Signature.hs:80-90
+    checks = [(proof.prR, z, (proof.prA, proof.prWa), 0), (proof.prR, y * z % R, (proof.prB, proof.prWb), 0),
+              (proof.prT, z, (t, proof.prWt), 1), (h.hscC, h.hscV, (sv, h.hscQv), 1)]
+    for (yi, zi), (ci, (si, wi)), (sip, wip, qi) in zip(yzs, h.hscS, h.hscW):
+        checks += [(ci, zi, (si, wi), 1), (ci, h.hscU, (sip, wip), 1), (h.hscC, yi, (sip, qi), 1)]
+    assert len(checks) == 3 * Q + 4
+    weights = [rng.randrange(1, R) for _ in checks]
+    D = bls.g1_decompress
+
+    def holds(A, B, Cs):
+        lhs = bls.g1_add(bls.g1_mul(D(A), alpha * x % R), bls.g1_mul(D(B), alpha))
+        rhs = bls.g1_add(bls.g1_mul(D(Cs[0]), S.fr_pow(x, -d + n)), bls.g1_mul(D(Cs[1]), S.fr_pow(x, 0)))
+        return lhs == rhs
+
+    A, B, Cs = gpu.pcv_fold(checks, weights)
+    assert holds(A, B, Cs)
+    # the fold equals the straightforward sums
+    accA = bls.INF
+    for (F, zi, (vi, Wi), grp), r in zip(checks, weights):
+        accA = bls.g1_add(accA, bls.g1_mul(D(Wi), r))
+    assert A == C(accA)
+    forged = list(checks)
+    F0, z0, (v0, W0), g0 = forged[2]
+    forged[2] = (F0, z0, ((v0 + 1) % R, W0), g0)
+    assert not holds(*gpu.pcv_fold(forged, weights))
+    with pytest.raises(gpu.SonicError):
+        gpu.pcv_fold([(bytes(48), 1, (1, bytes(48)), 0)], [1])

@@ -142,3 +142,37 @@ def test_wide_products_and_multiplier_variants(host):
                 out = (ctypes.c_uint32 * n)()
                 fn(op, _arr(a, n), _arr(b, n), _arr(c, n), _arr(d, n), out)
                 assert from_limbs(out) == want * Ri % p, (op, n)
+
+
+def test_g1_decompress_and_scalar_mul(host):
+    Rm = 1 << 384
+    Ri = pow(Rm, -1, Q)
+    rng = random.Random(35)
+
+    def aff_of(buf):
+        v = from_limbs(buf)
+        xm, ym = v & ((1 << 384) - 1), v >> 384
+        return None if xm == 0 and ym == 0 else (xm * Ri % Q, ym * Ri % Q)
+
+    pts = [None, bls.G1_GEN, bls.g1_neg(bls.G1_GEN)] + [bls.g1_mul_gen(rng.randrange(R)) for _ in range(12)]
+    for P in pts:
+        out = (ctypes.c_uint32 * 24)()
+        enc = bls.g1_compress(P)
+        assert host.ht_g1_decompress(enc, out) == 1
+        assert aff_of(out) == P
+    bad = [bytes(48), bytes([0xC0]) + bytes(46) + b"\x01", bytes([0x9F]) + b"\xff" * 47]
+    x = 1
+    while bls.fq_sqrt((x ** 3 + 4) % Q) is not None:
+        x += 1
+    bad.append(bytes([0x80 | (x >> 376)]) + (x & ((1 << 376) - 1)).to_bytes(47, "big"))  # x not on the curve
+    for enc in bad:
+        out = (ctypes.c_uint32 * 24)()
+        assert host.ht_g1_decompress(enc, out) == 0
+    for P in pts[1:6]:
+        for k in (0, 1, 2, R - 1, rng.randrange(R)):
+            am = _arr((P[0] * Rm % Q) | ((P[1] * Rm % Q) << 384), 24)
+            o = (ctypes.c_uint32 * 48)()
+            host.ht_g1_mul_scalar(am, _arr(k, 8), o)
+            a = (ctypes.c_uint32 * 24)()
+            host.ht_g1_to_affine(o, a)
+            assert aff_of(a) == bls.g1_mul(P, k)
