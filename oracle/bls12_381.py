@@ -281,3 +281,138 @@ def g1_from_raw(b: bytes):
     if x == 0 and y == 0:
         return INF
     return (x, y)
+
+
+# ======================================================================================
+# G2 over Fq2 = Fq[u]/(u^2 + 1): the h-vectors of the SRS (/root/reference/src/Sonic/SRS.hs:35-36,40-41)
+# Out of the prover's path (only pcV reads four of them); restated for the G2 fixed-base batch
+# that SURVEY.md section 8f lists as a "next" item.  E': y^2 = x^3 + 4(1 + u).
+# ======================================================================================
+G2_X = (0x024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8,
+        0x13e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e)
+G2_Y = (0x0ce5d527727d6e118cc9cdc6da2e351aadfd9baa8cbdd3a76d429a695160d12c923ac9cc3baca289e193548608b82801,
+        0x0606c4a02ea734cc32acd2b02bc28b99cb3e287e85a763af267492ab572e99ab3f370d275cec1da1aaa9075ff05f79be)
+G2_GEN = (G2_X, G2_Y)
+G2_B = (4, 4)
+
+
+def f2_add(a, b):
+    return ((a[0] + b[0]) % Q, (a[1] + b[1]) % Q)
+
+
+def f2_sub(a, b):
+    return ((a[0] - b[0]) % Q, (a[1] - b[1]) % Q)
+
+
+def f2_mul(a, b):
+    return ((a[0] * b[0] - a[1] * b[1]) % Q, (a[0] * b[1] + a[1] * b[0]) % Q)
+
+
+def f2_sqr(a):
+    return f2_mul(a, a)
+
+
+def f2_scale(a, k):
+    return (a[0] * k % Q, a[1] * k % Q)
+
+
+def f2_inv(a):
+    n = pow((a[0] * a[0] + a[1] * a[1]) % Q, Q - 2, Q)
+    return (a[0] * n % Q, (-a[1]) * n % Q)
+
+
+F2_ZERO, F2_ONE = (0, 0), (1, 0)
+
+
+def g2_is_on_curve(p) -> bool:
+    if p is INF:
+        return True
+    x, y = p
+    return f2_sqr(y) == f2_add(f2_mul(f2_sqr(x), x), G2_B)
+
+
+def _g2_jac_double(j):
+    X, Y, Z = j
+    if Z == F2_ZERO:
+        return (F2_ONE, F2_ONE, F2_ZERO)
+    A = f2_sqr(X)
+    B = f2_sqr(Y)
+    C = f2_sqr(B)
+    t = f2_add(X, B)
+    D = f2_scale(f2_sub(f2_sub(f2_sqr(t), A), C), 2)
+    E = f2_scale(A, 3)
+    F = f2_sqr(E)
+    X3 = f2_sub(F, f2_scale(D, 2))
+    Y3 = f2_sub(f2_mul(E, f2_sub(D, X3)), f2_scale(C, 8))
+    Z3 = f2_scale(f2_mul(Y, Z), 2)
+    return (X3, Y3, Z3)
+
+
+def _g2_jac_add(j1, j2):
+    X1, Y1, Z1 = j1
+    X2, Y2, Z2 = j2
+    if Z1 == F2_ZERO:
+        return j2
+    if Z2 == F2_ZERO:
+        return j1
+    Z1Z1, Z2Z2 = f2_sqr(Z1), f2_sqr(Z2)
+    U1, U2 = f2_mul(X1, Z2Z2), f2_mul(X2, Z1Z1)
+    S1, S2 = f2_mul(f2_mul(Y1, Z2), Z2Z2), f2_mul(f2_mul(Y2, Z1), Z1Z1)
+    if U1 == U2:
+        if S1 == S2:
+            return _g2_jac_double(j1)
+        return (F2_ONE, F2_ONE, F2_ZERO)
+    H = f2_sub(U2, U1)
+    I = f2_sqr(f2_scale(H, 2))
+    J = f2_mul(H, I)
+    r = f2_scale(f2_sub(S2, S1), 2)
+    V = f2_mul(U1, I)
+    X3 = f2_sub(f2_sub(f2_sqr(r), J), f2_scale(V, 2))
+    Y3 = f2_sub(f2_mul(r, f2_sub(V, X3)), f2_scale(f2_mul(S1, J), 2))
+    Z3 = f2_mul(f2_sub(f2_sub(f2_sqr(f2_add(Z1, Z2)), Z1Z1), Z2Z2), H)
+    return (X3, Y3, Z3)
+
+
+def _g2_to_jac(p):
+    return (F2_ONE, F2_ONE, F2_ZERO) if p is INF else (p[0], p[1], F2_ONE)
+
+
+def _g2_from_jac(j):
+    X, Y, Z = j
+    if Z == F2_ZERO:
+        return INF
+    zi = f2_inv(Z)
+    zi2 = f2_sqr(zi)
+    return (f2_mul(X, zi2), f2_mul(Y, f2_mul(zi2, zi)))
+
+
+def g2_add(p, q):
+    return _g2_from_jac(_g2_jac_add(_g2_to_jac(p), _g2_to_jac(q)))
+
+
+def g2_mul(p, k: int):
+    """`mul` on G2 (/root/reference/src/Sonic/SRS.hs:35-36,40-41)."""
+    k %= R
+    if k == 0 or p is INF:
+        return INF
+    acc = (F2_ONE, F2_ONE, F2_ZERO)
+    base = _g2_to_jac(p)
+    for bit in bin(k)[2:]:
+        acc = _g2_jac_double(acc)
+        if bit == "1":
+            acc = _g2_jac_add(acc, base)
+    return _g2_from_jac(acc)
+
+
+def g2_compress(p) -> bytes:
+    """ZCash-style 96-byte compressed G2: x.c1 || x.c0 big-endian; flags as for G1; the sign bit
+    is set when y is the lexicographically larger root (compare c1 first, then c0)."""
+    if p is INF:
+        return bytes([0xC0]) + bytes(95)
+    (x0, x1), (y0, y1) = p
+    b = bytearray(x1.to_bytes(48, "big") + x0.to_bytes(48, "big"))
+    b[0] |= 0x80
+    big = (y1 > (Q - 1) // 2) if y1 != 0 else (y0 > (Q - 1) // 2)
+    if big:
+        b[0] |= 0x20
+    return bytes(b)

@@ -166,6 +166,29 @@ class SRS:
     def gPositiveAlphaX(self) -> List[G1Bytes]:     # [i-1] = g^{alpha x^i}
         return self._range(FAMILY_ALPHA, 1, self.srsD)
 
+    def _range_g2(self, family: int, lo: int, count: int) -> List[bytes]:
+        out = ctypes.create_string_buffer(96 * count)
+        check(lib().sonic_srs_g2_range(self._h, family, lo, count, out))
+        raw = out.raw
+        return [raw[96 * i:96 * i + 96] for i in range(count)]
+
+    # the four G2 record fields (only with option "g2"); 96-byte compressed G2
+    @property
+    def hNegativeX(self) -> List[bytes]:
+        return self._range_g2(FAMILY_PLAIN, -self.srsD, self.srsD)[::-1]
+
+    @property
+    def hPositiveX(self) -> List[bytes]:
+        return self._range_g2(FAMILY_PLAIN, 0, self.srsD + 1)
+
+    @property
+    def hNegativeAlphaX(self) -> List[bytes]:
+        return self._range_g2(FAMILY_ALPHA, -self.srsD, self.srsD)[::-1]
+
+    @property
+    def hPositiveAlphaX(self) -> List[bytes]:  # [i] = h^{alpha x^i}, i = 0..d (h^alpha IS shared)
+        return self._range_g2(FAMILY_ALPHA, 0, self.srsD + 1)
+
     def free(self) -> None:
         if self._h:
             lib().sonic_srs_free(self._h)

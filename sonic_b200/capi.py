@@ -43,6 +43,7 @@ SYMBOLS = {
     "sonic_srs_load": (c_int, [c_char_p, POINTER(c_void_p)]),
     "sonic_srs_g1": (c_int, [c_void_p, c_int, c_int64, _u8p]),
     "sonic_srs_g1_range": (c_int, [c_void_p, c_int, c_int64, c_uint64, _u8p]),
+    "sonic_srs_g2_range": (c_int, [c_void_p, c_int, c_int64, c_uint64, _u8p]),
     "sonic_commit": (c_int, [c_void_p, c_int64, c_int64, c_uint64, _u8p, _u8p]),
     "sonic_open": (c_int, [c_void_p, _u8p, c_int64, c_uint64, _u8p, _u8p, _u8p]),
     "sonic_msm_g1": (c_int, [c_void_p, c_int, c_int64, c_uint64, _u8p, _u8p]),

@@ -273,7 +273,7 @@ int sonic_init(const int* devices, int ndev) {
         cx.sm_count = prop.multiProcessorCount;
         SONIC_CUDA(cudaStreamCreateWithFlags(&cx.stream, cudaStreamNonBlocking));
         for (auto& e : cx.ev) SONIC_CUDA(cudaEventCreate(&e));
-        if (const char* e = getenv("SONIC_ACC_BLOCKS")) { int v = atoi(e); if (v >= 2 && v <= 5) cx.opt_acc_blocks = v; }
+        if (const char* e = getenv("SONIC_ACC_BLOCKS")) { int v = atoi(e); if (v >= 2 && v <= 3) cx.opt_acc_blocks = v; }
         cx.ready = true;
     } catch (const CudaError& e) {
         cudaGetLastError();
@@ -354,6 +354,10 @@ int sonic_srs_new(uint64_t d, const uint8_t x[32], const uint8_t alpha[32], soni
         s->tables.stride = (uint32_t)npts;
         cudaError_t e = cudaMalloc((void**)&s->points, npts * levels * sizeof(G1Affine));
         if (e != cudaSuccess) { delete s; throw CudaError{e, "cudaMalloc(srs)", __LINE__}; }
+        if (cx.opt_g2) {
+            e = cudaMalloc(&s->g2_points, npts * g2_point_bytes());
+            if (e != cudaSuccess) { cudaFree(s->points); delete s; throw CudaError{e, "cudaMalloc(srs g2)", __LINE__}; }
+        }
         try {
             Timer tm(cx);
             uint8_t* h = pinned(cx, 64);
@@ -361,14 +365,31 @@ int sonic_srs_new(uint64_t d, const uint8_t x[32], const uint8_t alpha[32], soni
             memcpy(h + 32, alpha, 32);
             Fr* d_canon = cx.arena.get<Fr>(2);
             SONIC_CUDA(cudaMemcpyAsync(d_canon, h, 64, cudaMemcpyHostToDevice, cx.stream));
-            srs_generate(cx, d, d_canon, s->points, pre_c);
+            srs_generate(cx, d, d_canon, s->points, pre_c, s->g2_points);
             tm.stop();
         } catch (...) {
             cudaFree(s->points);
+            if (s->g2_points) cudaFree(s->g2_points);
             delete s;
             throw;
         }
         *out = s;
+        return (int)SONIC_OK;
+    });
+}
+
+int sonic_srs_g2_range(const sonic_srs* srs, int family, int64_t exponent, uint64_t count, uint8_t* out) {
+    if (!srs || !out || (family != SONIC_FAMILY_PLAIN && family != SONIC_FAMILY_ALPHA)) return fail(SONIC_ERR_INVALID_ARG, "bad argument");
+    if (!srs->g2_points) return fail(SONIC_ERR_INVALID_ARG, "this SRS was generated without its G2 vectors (option \"g2\")");
+    const int64_t d = (int64_t)srs->d;
+    if (count && (exponent < -d || exponent + (int64_t)count - 1 > d))
+        return fail(SONIC_ERR_SRS_TOO_SHORT, "pcV: h vector is not long enough: %" PRId64 " >= %" PRIu64, exponent < -d ? -exponent - 1 : exponent + (int64_t)count - 1, srs->d + 1);
+    if (!count) return SONIC_OK;
+    return guarded([&](Ctx& cx) {
+        uint8_t* d_out = cx.arena.get<uint8_t>(count * 96);
+        g2_compress_range(cx, srs->g2_points, srs->index(family, exponent), count, d_out);
+        SONIC_CUDA(cudaMemcpyAsync(out, d_out, count * 96, cudaMemcpyDeviceToHost, cx.stream));
+        SONIC_CUDA(cudaStreamSynchronize(cx.stream));
         return (int)SONIC_OK;
     });
 }
@@ -379,6 +400,7 @@ void sonic_srs_free(sonic_srs* srs) {
     std::lock_guard<std::mutex> lock(cx.mu);
     if (cx.ready) { cudaSetDevice(cx.device); cudaStreamSynchronize(cx.stream); }
     if (srs->points) cudaFree(srs->points);
+    if (srs->g2_points) cudaFree(srs->g2_points);
     delete srs;
 }
 
@@ -797,6 +819,8 @@ int sonic_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "window_bits")) {
         if (value != 0 && (value < 4 || value > 20)) return fail(SONIC_ERR_INVALID_ARG, "window_bits must be 0 or in [4, 20]");
         cx.opt_window_bits = (int)value;
+    } else if (!strcmp(name, "g2")) {
+        cx.opt_g2 = value != 0;
     } else if (!strcmp(name, "precompute")) {
         if (value != -1 && value != 0 && (value < 4 || value > 20)) return fail(SONIC_ERR_INVALID_ARG, "precompute must be -1 (auto), 0 (off) or window bits in [4, 20]");
         cx.opt_precompute = (int)value;
@@ -809,11 +833,8 @@ int sonic_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "reduce_k")) {
         if (value < 1 || value > 256) return fail(SONIC_ERR_INVALID_ARG, "reduce_k must be in [1, 256]");
         cx.opt_reduce_k = (int)value;
-    } else if (!strcmp(name, "reduce_blocks")) {
-        if (value < 2 || value > 4) return fail(SONIC_ERR_INVALID_ARG, "reduce_blocks must be in [2, 4]");
-        cx.opt_reduce_blocks = (int)value;
     } else if (!strcmp(name, "acc_blocks")) {
-        if (value < 2 || value > 5) return fail(SONIC_ERR_INVALID_ARG, "acc_blocks must be in [2, 5]");
+        if (value < 2 || value > 3) return fail(SONIC_ERR_INVALID_ARG, "acc_blocks must be 2 or 3");
         cx.opt_acc_blocks = (int)value;
     } else if (!strcmp(name, "chunk")) {
         if (value < 0 || value > 4096) return fail(SONIC_ERR_INVALID_ARG, "chunk must be in [0, 4096]");

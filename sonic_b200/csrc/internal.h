@@ -45,7 +45,11 @@ void exclusive_scan_u32(Arena& ar, const uint32_t* in, uint32_t* out, uint32_t n
 // ---- srs.cu ------------------------------------------------------------------------------
 // Generates the resident point array.  d_canon: x, alpha canonical (2 Fr) in device memory.
 // pre_c > 0 additionally fills levels 1..W-1 with the 2^(pre_c j) multiples (W = ceil(255/pre_c)).
-void srs_generate(Ctx& cx, uint64_t d, const Fr* d_canon, G1Affine* d_points, int pre_c);
+// d_g2_points (nullable): also fills the G2 h-vectors, 2*(2d+1) affine G2 points, same exponent indexing, no hole.
+void srs_generate(Ctx& cx, uint64_t d, const Fr* d_canon, G1Affine* d_points, int pre_c, void* d_g2_points = nullptr);
+void srs_generate_g2(Ctx& cx, const Fr* scal_m, uint64_t npts, void* d_g2_points);
+void g2_compress_range(Ctx& cx, const void* d_g2_points, uint64_t first, uint64_t count, uint8_t* d_out);
+size_t g2_point_bytes();
 
 // ---- poly.cu -----------------------------------------------------------------------------
 struct OpenJob {
@@ -118,6 +122,7 @@ struct sonic_srs {
     uint64_t d = 0;
     sonic::G1Affine* points = nullptr;  // levels x 2*(2d+1) affine points, Montgomery form; level 0 is the SRS
     sonic::MsmTables tables;            // precomputed window multiples (c == 0: level 0 only)
+    void* g2_points = nullptr;          // optional: 2*(2d+1) affine G2 points (the h-vectors), Montgomery form
     uint64_t stride() const { return 2 * d + 1; }
     uint64_t index(int family, int64_t k) const { return (uint64_t)family * stride() + (uint64_t)(k + (int64_t)d); }
 };

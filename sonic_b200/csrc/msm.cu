@@ -469,9 +469,7 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const u
         if (K < 1) K = 1;
         const uint32_t S = div_up(p.B, (uint64_t)MSM_RED_THREADS * K);
         G1XYZZ* partial = ar.get<G1XYZZ>((size_t)M * p.sets * S);
-        if (cx.opt_reduce_blocks >= 4) SONIC_LAUNCH(k_msm_bucket_reduce<4>, dim3(S, (unsigned)(M * p.sets)), MSM_RED_THREADS, 0, buckets, p.B, K, partial);
-        else if (cx.opt_reduce_blocks == 3) SONIC_LAUNCH(k_msm_bucket_reduce<3>, dim3(S, (unsigned)(M * p.sets)), MSM_RED_THREADS, 0, buckets, p.B, K, partial);
-        else SONIC_LAUNCH(k_msm_bucket_reduce<2>, dim3(S, (unsigned)(M * p.sets)), MSM_RED_THREADS, 0, buckets, p.B, K, partial);
+        SONIC_LAUNCH(k_msm_bucket_reduce<2>, dim3(S, (unsigned)(M * p.sets)), MSM_RED_THREADS, 0, buckets, p.B, K, partial);
         SONIC_LAUNCH(k_msm_finish, M, 64, 0, partial, S, p.sets, p.c, d_out_aff, d_out_comp);
     } else {
     // level-by-level reduction of every bucket set to one point

@@ -159,7 +159,7 @@ static int srs_table_bits(uint64_t npoints) {
 // Generates the resident point array.  d_canon: x, alpha canonical (2 Fr) in device memory.
 // Level 0 is the SRS itself; with pre_c > 0, level j holds the same points times 2^(pre_c j),
 // obtained from the same fixed-base table with the scalar multiplied by 2^(pre_c j) mod r.
-void srs_generate(Ctx& cx, uint64_t d, const Fr* d_canon, G1Affine* d_points, int pre_c) {
+void srs_generate(Ctx& cx, uint64_t d, const Fr* d_canon, G1Affine* d_points, int pre_c, void* d_g2_points) {
     Arena& ar = cx.arena;
     const uint64_t stride = 2 * d + 1, npts = 2 * stride;
     const int levels = pre_c > 0 ? (255 + pre_c - 1) / pre_c : 1;
@@ -186,6 +186,7 @@ void srs_generate(Ctx& cx, uint64_t d, const Fr* d_canon, G1Affine* d_points, in
         SONIC_LAUNCH(k_fixed_base, div_up(npts, 128), 128, 0, scal, Ta, w, Wt, npts, hole, px);
         SONIC_LAUNCH(k_batch_affine, div_up(div_up(npts, AFF_BATCH), 128), 128, 0, px, d_points + (size_t)j * npts, npts);
     }
+    if (d_g2_points) srs_generate_g2(cx, scal_m, npts, d_g2_points);
 }
 
 }  // namespace sonic

@@ -4,6 +4,7 @@
 #include <cstring>
 #include "../../sonic_b200/csrc/g1.cuh"
 #include "../../sonic_b200/csrc/scalar.cuh"
+#include "../../sonic_b200/csrc/g2.cuh"
 
 using namespace sonic;
 
@@ -108,6 +109,20 @@ void ht_g1_mul_scalar(const uint32_t* aff, const uint32_t* k8, uint32_t* out_xyz
     stx(out_xyzz, g1_mul_scalar(lda(aff), ld<Fr>(k8)));
 }
 void ht_g1_gen(uint32_t* out) { sta(out, G1Affine::gen()); }
+
+// k * G2 generator by double-and-add with the device formulas -> 96-byte compressed
+void ht_g2_mul_gen(const uint32_t* k8, uint8_t* out96) {
+    Fr k = ld<Fr>(k8);
+    G2XYZZ r = G2XYZZ::inf();
+    const G2Affine g = G2Affine::gen();
+    bool started = false;
+    for (int i = 7; i >= 0; --i)
+        for (int b = 31; b >= 0; --b) {
+            if (started) r = g2_dbl(r);
+            if ((k.l[i] >> b) & 1) { g2_madd(r, g); started = true; }
+        }
+    g2_compress(g2_to_affine(r), out96);
+}
 
 // signed-digit recoding of a canonical scalar: returns W digits
 int ht_recode(const uint32_t* scalar8, int c, int32_t* digits) {

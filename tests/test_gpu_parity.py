@@ -331,3 +331,45 @@ def test_pcv_fold_batches_the_verifier_checks(gpu):
     assert not holds(*gpu.pcv_fold(forged, weights))
     with pytest.raises(gpu.SonicError):
         gpu.pcv_fold([(bytes(48), 1, (1, bytes(48)), 0)], [1])
+
+
+def test_prove_with_more_than_64_msms(gpu):
+    """Q = 17 gives 4Q+7 = 75 MSMs: more than one batch of the MSM pipeline (64 jobs per launch)."""
+    rng = random.Random(23)
+    circuit, assignment = rnd_circuit(rng, n=18, m=17)
+    n, Q = 18, 17
+    d = 7 * n + 3
+    x, alpha = rng.randrange(1, R), rng.randrange(1, R)
+    g, o = _srs_pair(gpu, d, x, alpha)
+    gc, ga = to_gpu_types(gpu, circuit, assignment)
+    rnd = [rng.randrange(1, R) for _ in range(S.rnd_count(Q))]
+    want, (y, z, yzs) = S.prove_dense(o, assignment, circuit, rnd)
+    got = gpu.prove_bytes(g, ga, gc, rnd)
+    assert got == S.encode_proof(want)
+    # the same proof assembled from two shards (both sharding modes are functions of the sizes only)
+    blobs = [gpu.prove_shard(g, ga, gc, rnd, r, 2) for r in range(2)]
+    assert gpu.prove_combine(Q, blobs) == got
+    blobs = [gpu.prove_shard(g, ga, gc, rnd, r, 3) for r in range(3)]
+    assert gpu.prove_combine(Q, blobs) == got
+
+
+def test_srs_g2_vectors(gpu):
+    """the h-vectors of SRS.new (SRS.hs:35-36,40-41) from the G2 fixed-base batch."""
+    rng = random.Random(24)
+    d = 11
+    x, alpha = rng.randrange(1, R), rng.randrange(1, R)
+    try:
+        gpu.set_option("g2", 1)
+        g = gpu.SRS.new(d, x, alpha)
+    finally:
+        gpu.set_option("g2", 0)
+    xi = pow(x, -1, R)
+    H = bls.G2_GEN
+    c2 = bls.g2_compress
+    assert g.hPositiveX == [c2(bls.g2_mul(H, pow(x, i, R))) for i in range(0, d + 1)]
+    assert g.hNegativeX == [c2(bls.g2_mul(H, pow(xi, i, R))) for i in range(1, d + 1)]
+    assert g.hPositiveAlphaX == [c2(bls.g2_mul(H, alpha * pow(x, i, R) % R)) for i in range(0, d + 1)]
+    assert g.hNegativeAlphaX == [c2(bls.g2_mul(H, alpha * pow(xi, i, R) % R)) for i in range(1, d + 1)]
+    g1only = gpu.SRS.new(d, x, alpha)
+    with pytest.raises(gpu.SonicError):
+        g1only.hPositiveX

@@ -176,3 +176,15 @@ def test_g1_decompress_and_scalar_mul(host):
             a = (ctypes.c_uint32 * 24)()
             host.ht_g1_to_affine(o, a)
             assert aff_of(a) == bls.g1_mul(P, k)
+
+
+def test_g2_arithmetic_and_encoding(host):
+    rng = random.Random(36)
+    for k in [1, 2, 3, R - 1, 0] + [rng.randrange(R) for _ in range(6)]:
+        out = (ctypes.c_uint8 * 96)()
+        host.ht_g2_mul_gen(_arr(k, 8), out)
+        assert bytes(out) == bls.g2_compress(bls.g2_mul(bls.G2_GEN, k)), k
+    # the public ZCash encoding of the G2 generator
+    out = (ctypes.c_uint8 * 96)()
+    host.ht_g2_mul_gen(_arr(1, 8), out)
+    assert bytes(out).hex().startswith("93e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049")
