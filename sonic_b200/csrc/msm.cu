@@ -22,8 +22,14 @@
 //   5. fix-up       : one thread per straddling bucket folds its pieces; buckets with more
 //                     than HEAVY pieces (skewed scalars: zeros, +-1) are folded by a whole
 //                     block each.
-//   6. bucket reduce: sum_b (b+1) * B_b per window by segmented running sums + block tree.
-//   7. finish       : per job, Horner over the windows, one inversion, affine + compressed.
+//   6. bucket reduce: sum_b (b+1) * B_b per bucket set by segmented running sums + block tree
+//                     (option reduce_mode=1: level by level, no per-thread scalar multiple).
+//   7. finish       : per job, fold of the partials (Horner over the windows when every window
+//                     has its own bucket set), one inversion, affine + compressed.
+//
+// With the precomputed window multiples of the SRS (MsmTables: level j of the point array holds
+// 2^(c j) * P) all windows of a job share ONE bucket set and the window index selects the
+// table level: W-fold fewer buckets to sort, reduce and fold, and no doubling tail.
 #include "internal.h"
 #include "g1io.cuh"
 #include "scalar.cuh"
@@ -348,7 +354,7 @@ k_msm_finish(const G1XYZZ* __restrict__ partial, uint32_t S, int W, int c, G1Aff
 // ---- host side ---------------------------------------------------------------------------
 struct MsmPlan {
     int c, W, sets;
-    uint32_t B, GB, L, K, S, n_tot;
+    uint32_t B, GB, L, n_tot;
 };
 
 static MsmPlan msm_plan(const Ctx& cx, uint32_t n_tot, int M, const MsmTables& tables) {
@@ -381,17 +387,6 @@ static MsmPlan msm_plan(const Ctx& cx, uint32_t n_tot, int M, const MsmTables& t
     if (L < 8) L = 8;
     if (L > 64) L = 64;
     p.L = cx.opt_chunk > 0 ? (uint32_t)cx.opt_chunk : (uint32_t)L;
-    // buckets per thread in the reduction: each thread pays ~25 extra point operations (its
-    // offset multiple and the block tree) on top of 2 per bucket, so K is as large as the
-    // machine fill allows
-    uint64_t all_buckets = (uint64_t)p.GB;
-    uint64_t kfill = all_buckets / ((uint64_t)cx.sm_count * MSM_RED_THREADS);  // about one block per SM
-    p.K = (uint32_t)kfill;
-    if (p.K < 8) p.K = 8;
-    if (p.K > 64) p.K = 64;
-    if (p.K > p.B / MSM_RED_THREADS) p.K = p.B / MSM_RED_THREADS;
-    if (p.K < 1) p.K = 1;
-    p.S = div_up(p.B, (uint64_t)MSM_RED_THREADS * p.K);
     return p;
 }
 

@@ -373,3 +373,44 @@ def test_srs_g2_vectors(gpu):
     g1only = gpu.SRS.new(d, x, alpha)
     with pytest.raises(gpu.SonicError):
         g1only.hPositiveX
+
+
+def test_prove_degenerate_inputs(gpu):
+    """Edge cases: Q = 1; an all-zero assignment (r'(X,1) is the four blinders only, most MSM scalars
+    are zero); zero blinders; hscProve with no (y, z) pairs at all."""
+    rng = random.Random(25)
+    x, alpha = rng.randrange(1, R), rng.randrange(1, R)
+    # Q = 1, n = 3
+    circuit, assignment = rnd_circuit(rng, n=3, m=1)
+    g, o = _srs_pair(gpu, 25, x, alpha)
+    gc, ga = to_gpu_types(gpu, circuit, assignment)
+    rnd = [rng.randrange(1, R) for _ in range(S.rnd_count(1))]
+    assert gpu.prove_bytes(g, ga, gc, rnd) == S.encode_proof(S.prove_dense(o, assignment, circuit, rnd)[0])
+    # all-zero assignment satisfies any circuit with cs = 0; blinders zero as well
+    n, Q = 4, 3
+    w = [[rng.randrange(R) for _ in range(n)] for _ in range(Q)]
+    circuit = S.ArithCircuit(S.GateWeights(w, [list(r) for r in w], [list(r) for r in w]), [0] * Q)
+    assignment = S.Assignment([0] * n, [0] * n, [0] * n)
+    g, o = _srs_pair(gpu, 7 * n + 5, x, alpha)
+    gc, ga = to_gpu_types(gpu, circuit, assignment)
+    for blind in (True, False):
+        rnd = [rng.randrange(1, R) for _ in range(S.rnd_count(Q))]
+        if not blind:
+            rnd[0:4] = [0, 0, 0, 0]
+        want, (y, z, yzs) = S.prove_dense(o, assignment, circuit, rnd)
+        got = gpu.prove_bytes(g, ga, gc, rnd)
+        assert got == S.encode_proof(want)
+        assert S.verify_trapdoor(o, circuit, S.decode_proof(got, Q), y, z, yzs)
+        if not blind:
+            assert want.prR is bls.INF  # r'(X,1) = 0: the commitment is the identity
+    # a zero challenge is `recip 0` (every challenge evaluates a polynomial with negative powers)
+    rnd[5] = 0
+    with pytest.raises(gpu.SonicError) as e:
+        gpu.prove_bytes(g, ga, gc, rnd)
+    assert e.value.kind == "DIV_BY_ZERO"
+    # hscProve with an empty list of pairs
+    u, v = rng.randrange(1, R), rng.randrange(1, R)
+    sXY = S.sPoly(circuit.weights)
+    want = S.hscProve(o, sXY, [], u, v)
+    got = gpu.hscProve(g, gc, [], u, v)
+    assert (got.hscS, got.hscW, got.hscQv, got.hscC) == ([], [], C(want.hscQv), C(want.hscC))
