@@ -207,7 +207,7 @@ def main() -> None:
         return float(t.item())
 
     # ---- roofline denominator: measured integer-multiply peak on this device ---------------------
-    peaks = [L.sonic_imad_peak_lmacs(v, 3000) for v in (0, 1, 2)]
+    peaks = [L.sonic_imad_peak_lmacs(v, 3000) for v in (0, 1, 2, 3)]
     imad_peak = max(peaks)
 
     # ---- workload -----------------------------------------------------------------------------------
@@ -248,17 +248,27 @@ def main() -> None:
         part_t = torch.empty(nm * 96, dtype=torch.uint8, device="cuda")
         gath_t = torch.empty(world * nm * 96, dtype=torch.uint8, device="cuda")
 
+    phase = {"shard": 0.0, "exchange": 0.0, "combine": 0.0, "calls": 0}
+
     def exchange_and_combine() -> bytes:
+        t0 = time.perf_counter()
         dist.all_gather_into_tensor(gath_t, part_t)
         torch.cuda.current_stream().synchronize()
+        t1 = time.perf_counter()
         capi.check(L.sonic_prove_combine_device(Q, world, gath_t.data_ptr(), out, proof_buf, proof_size, ctypes.byref(written)))
+        t2 = time.perf_counter()
+        phase["exchange"] += t1 - t0
+        phase["combine"] += t2 - t1
+        phase["calls"] += 1
         return proof_buf.raw
 
     def step_resident() -> bytes:
         if world == 1:
             capi.check(L.sonic_prove_device(srs._h, ch, d_in, d_rnd, hrnd, out, len(out), ctypes.byref(written)))
             return out.raw[:proof_size]
+        t0 = time.perf_counter()
         capi.check(L.sonic_prove_shard_sink(srs._h, ch, d_in, 1, d_rnd, hrnd, rank, world, out, len(out), ctypes.byref(written), part_t.data_ptr()))
+        phase["shard"] += time.perf_counter() - t0
         return exchange_and_combine()
 
     def step_e2e() -> bytes:
@@ -285,6 +295,10 @@ def main() -> None:
 
     sampler = ClockSampler(local_rank)   # started before the warm-up so that NVML start-up is not in the timed region
     sampler.start()
+    if world > 1:
+        for _ in range(20):               # NCCL sets its channels up lazily: keep that out of the timed steps
+            dist.all_gather_into_tensor(gath_t, part_t)
+        torch.cuda.synchronize()
     for _ in range(args.warmup):
         p_res = step_resident()
     for _ in range(args.warmup):
@@ -296,6 +310,8 @@ def main() -> None:
         capi.check(L.sonic_prove(srs._h, ch, hin, hin + n * 32, hin + 2 * n * 32, hrnd, out, len(out), ctypes.byref(written)))
         if out.raw[:proof_size] != p_res:
             raise SystemExit("sharded proof differs from the single-GPU proof")
+    for k in phase:
+        phase[k] = 0.0 if k != "calls" else 0
     ev_ms, wall_ms, launches, proof = timed(step_resident, args.steps)
     stage = {k: sb.last_timing_ms(k) for k in ("msm", "msm.sort", "msm.accumulate", "msm.accumulate_kernel", "msm.reduce", "poly", "total",
                                                "msm.window_bits", "msm.windows", "msm.terms", "msm.entries", "msm.chunk", "msm.buckets")}
@@ -336,7 +352,8 @@ def main() -> None:
                      "window_bits": stage["msm.window_bits"], "windows": stage["msm.windows"], "entries": stage["msm.entries"]},
         "kernel_ms": acc_ms, "msm_ms": stage["msm"], "kernel_share_of_step": acc_ms / ms_per_step if ms_per_step else None,
         "whole_msm_frac": (canon_lmac / (stage["msm"] * 1e-3)) / imad_peak if stage["msm"] > 0 and imad_peak else None,
-        "imad_microbench_lmacs": {"mad.lo.cc+madc.hi": peaks[0], "mad.wide.u32": peaks[1], "mad.lo+mad.hi": peaks[2]},
+        "imad_microbench_lmacs": {"mad.lo.cc+madc.hi": peaks[0], "mad.wide.u32": peaks[1], "mad.lo+mad.hi": peaks[2],
+                                  "carry-chained rows (madc.lo.cc/madc.hi.cc x4)": peaks[3]},
         "hbm": {"algorithmic_gb_per_s": stage["msm.entries"] * 100.0 / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None,
                 "peak_gb_per_s": hbm_peak, "note": "96 B base + 4 B entry per insertion; not the bound"},
     }
@@ -463,6 +480,9 @@ def main() -> None:
             "gpu_launches": launches,
             "wall_ms_per_step": wall_ms / args.steps,
             "stages_ms_last_step": {k: stage[k] for k in ("poly", "msm.sort", "msm.accumulate", "msm.reduce", "msm", "total")},
+            "shard_phases_ms_rank0": None if world == 1 or not phase["calls"] else {
+                "shard_call": 1e3 * phase["shard"] / max(1, args.steps), "exchange": 1e3 * phase["exchange"] / phase["calls"],
+                "combine": 1e3 * phase["combine"] / phase["calls"], "note": "host wall clock on rank 0 over the timed steps (exchange/combine: both timed regions)"},
             "roofline": roofline,
             "cpu_baseline": cpu,
             "msm_sweep": sweep,

@@ -95,6 +95,8 @@ __global__ void k_sum_raw(const Fq* __restrict__ raw, uint32_t n, uint8_t* __res
 //   variant 0: mad.lo.cc / madc.hi.cc pairs (what the field multiplier issues; IMAD.WIDE.U32 + carry)
 //   variant 1: mad.wide.u32 on a 64-bit accumulator (IMAD.WIDE.U32, no carry)
 //   variant 2: separate mad.lo.u32 and mad.hi.u32 (two IMADs per product)
+//   variant 3: four products chained through the carry flag, as one row of the multiplier is
+//              (mad.lo.cc / madc.hi.cc / madc.lo.cc / ... : IMAD.WIDE.U32.X with carry in AND out)
 template <int VARIANT>
 __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* out, uint32_t seed, int iters) {
     uint32_t lo[8], hi[8], m[8];
@@ -115,11 +117,22 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* out, uint32_t seed,
                     asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(lo[k]), "r"(m[k]));
                     lo[k] = (uint32_t)acc;
                     hi[k] = (uint32_t)(acc >> 32);
-                } else {
+                } else if (VARIANT == 2) {
                     uint32_t nl, nh;
                     asm volatile("mad.lo.u32 %0, %2, %3, %4; mad.hi.u32 %1, %2, %3, %5;"
                                  : "=&r"(nl), "=r"(nh) : "r"(lo[k]), "r"(m[k]), "r"(lo[k]), "r"(hi[k]));
                     lo[k] = nl; hi[k] = nh;
+                }
+            }
+            if (VARIANT == 3) {
+                // two carry chains of four products each (8 products, like the other variants)
+#pragma unroll
+                for (int h = 0; h < 8; h += 4) {
+                    Chain::mad_wide_cc(lo[h], hi[h], lo[h], m[h], lo[h], hi[h]);
+                    Chain::madc_wide_cc(lo[h + 1], hi[h + 1], lo[h + 1], m[h + 1], lo[h + 1], hi[h + 1]);
+                    Chain::madc_wide_cc(lo[h + 2], hi[h + 2], lo[h + 2], m[h + 2], lo[h + 2], hi[h + 2]);
+                    Chain::madc_wide_cc(lo[h + 3], hi[h + 3], lo[h + 3], m[h + 3], lo[h + 3], hi[h + 3]);
+                    hi[h + 3] = Chain::addc(hi[h + 3], 0);
                 }
             }
         }
@@ -274,6 +287,7 @@ int sonic_init(const int* devices, int ndev) {
         SONIC_CUDA(cudaStreamCreateWithFlags(&cx.stream, cudaStreamNonBlocking));
         for (auto& e : cx.ev) SONIC_CUDA(cudaEventCreate(&e));
         if (const char* e = getenv("SONIC_ACC_BLOCKS")) { int v = atoi(e); if (v >= 2 && v <= 3) cx.opt_acc_blocks = v; }
+        if (const char* e = getenv("SONIC_ACC_MODE")) { int v = atoi(e); if (v >= 0 && v <= 1) cx.opt_acc_mode = v; }
         cx.ready = true;
     } catch (const CudaError& e) {
         cudaGetLastError();
@@ -833,6 +847,9 @@ int sonic_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "reduce_k")) {
         if (value < 1 || value > 256) return fail(SONIC_ERR_INVALID_ARG, "reduce_k must be in [1, 256]");
         cx.opt_reduce_k = (int)value;
+    } else if (!strcmp(name, "acc_mode")) {
+        if (value < 0 || value > 1) return fail(SONIC_ERR_INVALID_ARG, "acc_mode must be 0 or 1");
+        cx.opt_acc_mode = (int)value;
     } else if (!strcmp(name, "acc_blocks")) {
         if (value < 2 || value > 3) return fail(SONIC_ERR_INVALID_ARG, "acc_blocks must be 2 or 3");
         cx.opt_acc_blocks = (int)value;
@@ -884,7 +901,8 @@ double sonic_imad_peak_lmacs(int variant, int iters) {
             SONIC_CUDA(cudaEventRecord(cx.ev[4], cx.stream));
             if (variant == 0) SONIC_LAUNCH(k_imad_peak<0>, blocks, threads, 0, out, 12345u, iters);
             else if (variant == 1) SONIC_LAUNCH(k_imad_peak<1>, blocks, threads, 0, out, 12345u, iters);
-            else SONIC_LAUNCH(k_imad_peak<2>, blocks, threads, 0, out, 12345u, iters);
+            else if (variant == 2) SONIC_LAUNCH(k_imad_peak<2>, blocks, threads, 0, out, 12345u, iters);
+            else SONIC_LAUNCH(k_imad_peak<3>, blocks, threads, 0, out, 12345u, iters);
             SONIC_CUDA(cudaEventRecord(cx.ev[5], cx.stream));
             SONIC_CUDA(cudaStreamSynchronize(cx.stream));
             float ms = 0;

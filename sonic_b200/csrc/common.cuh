@@ -113,6 +113,7 @@ struct Ctx {
     uint64_t launches = 0;
     int opt_window_bits = 0;
     int opt_chunk = 0;
+    int opt_acc_mode = 0;                                 // 0 straight-line mixed addition in registers, 1 compact (operand file in shared memory)
     bool opt_g2 = false;                                  // SRS.new also generates the G2 h-vectors
     int opt_reduce_mode = 0;                              // 0 flat (K buckets per thread + block tree), 1 level by level
     int opt_reduce_k = 64;

@@ -430,10 +430,27 @@ __global__ void k_points_to_raw(const G1Affine* __restrict__ pts, uint32_t n, Fq
     out[2 * i + 1] = fp_from_mont(pts[i].y);
 }
 
-// out48[m] = compress(sum_r raw[r][m]),  raw laid out [world][nm] x 96 B
+// out48[m] = compress(sum_r raw[r][m]),  raw laid out [world][nm] x 96 B.  When at most one rank
+// contributes (whole MSMs dealt to ranks: everybody else holds the identity) the point is already
+// affine and is only re-encoded: no addition, no second inversion.
 __global__ void k_fold_partials(const Fq* __restrict__ raw, uint32_t nm, uint32_t world, uint8_t* __restrict__ out48) {
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nm) return;
+    uint32_t contributors = 0;
+    G1Affine only = G1Affine::inf();
+    for (uint32_t r = 0; r < world; ++r) {
+        const Fq* p = raw + 2 * ((size_t)r * nm + m);
+        if (!(p[0].is_zero() && p[1].is_zero())) {
+            ++contributors;
+            only.x = p[0];
+            only.y = p[1];
+        }
+    }
+    if (contributors <= 1) {
+        if (contributors) { only.x = fp_to_mont(only.x); only.y = fp_to_mont(only.y); }
+        g1_compress(only, out48 + (size_t)m * 48);
+        return;
+    }
     G1XYZZ acc = G1XYZZ::inf();
     for (uint32_t r = 0; r < world; ++r) {
         const Fq* p = raw + 2 * ((size_t)r * nm + m);
