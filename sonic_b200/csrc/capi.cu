@@ -845,7 +845,7 @@ int sonic_set_option(const char* name, int64_t value) {
         if (value < 0 || value > 1) return fail(SONIC_ERR_INVALID_ARG, "reduce_mode must be 0 or 1");
         cx.opt_reduce_mode = (int)value;
     } else if (!strcmp(name, "reduce_k")) {
-        if (value < 1 || value > 256) return fail(SONIC_ERR_INVALID_ARG, "reduce_k must be in [1, 256]");
+        if (value < 0 || value > 256) return fail(SONIC_ERR_INVALID_ARG, "reduce_k must be in [0, 256]");
         cx.opt_reduce_k = (int)value;
     } else if (!strcmp(name, "acc_mode")) {
         if (value < 0 || value > 1) return fail(SONIC_ERR_INVALID_ARG, "acc_mode must be 0 or 1");

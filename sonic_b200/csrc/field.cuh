@@ -236,6 +236,37 @@ SONIC_HD Fp<P> fp_mul_unrolled(const Fp<P>& a, const Fp<P>& b) {
     return r;
 }
 
+// Two independent products with their rows interleaved: four carry chains in flight instead of
+// two, so that a scheduler with few resident warps still finds a ready IMAD while the previous
+// one's carry is in flight (ncu: the accumulate kernel's top stall is `wait` on IMAD.WIDE.U32.X).
+template <class P>
+SONIC_HD void fp_mul2(const Fp<P>& a1, const Fp<P>& b1, const Fp<P>& a2, const Fp<P>& b2, Fp<P>& r1, Fp<P>& r2) {
+    constexpr int N = P::N;
+    static_assert(N % 2 == 0, "even limb count");
+    uint32_t e1[N], o1[N], e2[N], o2[N];
+    mont_row_first<P>(e1, o1, a1.l, b1.l[0]);
+    mont_row_first<P>(e2, o2, a2.l, b2.l[0]);
+#pragma unroll
+    for (int i = 1; i < N; i += 2) {
+        mont_row_next<P>(e1, o1, a1.l, b1.l[i]);
+        mont_row_next<P>(e2, o2, a2.l, b2.l[i]);
+        if (i + 1 < N) {
+            mont_row_next<P>(o1, e1, a1.l, b1.l[i + 1]);
+            mont_row_next<P>(o2, e2, a2.l, b2.l[i + 1]);
+        }
+    }
+    r1.l[0] = Chain::add_cc(o1[1], e1[0]);
+#pragma unroll
+    for (int k = 1; k < N - 1; ++k) r1.l[k] = Chain::addc_cc(o1[k + 1], e1[k]);
+    r1.l[N - 1] = Chain::addc(e1[N - 1], 0);
+    r2.l[0] = Chain::add_cc(o2[1], e2[0]);
+#pragma unroll
+    for (int k = 1; k < N - 1; ++k) r2.l[k] = Chain::addc_cc(o2[k + 1], e2[k]);
+    r2.l[N - 1] = Chain::addc(e2[N - 1], 0);
+    fp_reduce_once(r1);
+    fp_reduce_once(r2);
+}
+
 // Rolled variant: the same rows, two per loop iteration (so the accumulator roles return to
 // where they started), the multiplier limbs rotated through registers.  Same IMAD count, one
 // sixth of the code: a point addition then fits the instruction cache, which the fully

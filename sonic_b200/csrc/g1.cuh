@@ -11,6 +11,11 @@
 #pragma once
 #include "field.cuh"
 
+// 1: the mixed addition issues its independent products in interleaved pairs (fp_mul2)
+#ifndef SONIC_MADD_PAIRED
+#define SONIC_MADD_PAIRED 0
+#endif
+
 namespace sonic {
 
 struct G1Affine {
@@ -82,6 +87,30 @@ SONIC_HD G1XYZZ g1_dbl(const G1XYZZ& p) {
 SONIC_HD void g1_madd(G1XYZZ& acc, const G1Affine& a) {
     if (a.is_inf()) return;
     if (acc.is_inf()) { acc = G1XYZZ::from_affine(a); return; }
+#if SONIC_MADD_PAIRED
+    // independent products issued in pairs with interleaved rows (fp_mul2)
+    Fq U2, S2;
+    fp_mul2(a.x, acc.zz, a.y, acc.zzz, U2, S2);
+    Fq P = fp_sub(U2, acc.x);
+    Fq R = fp_sub(S2, acc.y);
+    if (P.is_zero()) {
+        if (R.is_zero()) acc = g1_mdbl(a);
+        else acc = G1XYZZ::inf();
+        return;
+    }
+    Fq PP, RR;
+    fp_mul2(P, P, R, R, PP, RR);
+    Fq PPP, Q;
+    fp_mul2(P, PP, acc.x, PP, PPP, Q);
+    Fq X3 = fp_sub(fp_sub(RR, PPP), fp_dbl(Q));
+    Fq Y3 = fp_mul_sub2(R, fp_sub(Q, X3), acc.y, PPP);
+    acc.x = X3;
+    acc.y = Y3;
+    Fq zz3, zzz3;
+    fp_mul2(acc.zz, PP, acc.zzz, PPP, zz3, zzz3);
+    acc.zz = zz3;
+    acc.zzz = zzz3;
+#else
     Fq U2 = fp_mul(a.x, acc.zz);
     Fq S2 = fp_mul(a.y, acc.zzz);
     Fq P = fp_sub(U2, acc.x);
@@ -100,6 +129,7 @@ SONIC_HD void g1_madd(G1XYZZ& acc, const G1Affine& a) {
     acc.y = Y3;
     acc.zz = fp_mul(acc.zz, PP);
     acc.zzz = fp_mul(acc.zzz, PPP);
+#endif
 }
 
 // acc += b   (full addition)

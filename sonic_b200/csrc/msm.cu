@@ -563,12 +563,17 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const u
     G1XYZZ* head = ar.get<G1XYZZ>(chunks ? chunks : 1);
     G1XYZZ* tail = ar.get<G1XYZZ>(chunks ? chunks : 1);
     SONIC_CUDA(cudaEventRecord(cx.ev[8], st));
-    if (chunks) {
-        if (cx.opt_acc_blocks == 5) SONIC_LAUNCH(k_msm_accumulate<5>, div_up(chunks, 128), 128, 0, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
-        else if (cx.opt_acc_blocks == 4) SONIC_LAUNCH(k_msm_accumulate<4>, div_up(chunks, 128), 128, 0, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
-        else if (cx.opt_acc_blocks == 2) SONIC_LAUNCH(k_msm_accumulate<2>, div_up(chunks, 128), 128, 0, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
-        else if (cx.opt_acc_blocks == 3) SONIC_LAUNCH(k_msm_accumulate<3>, div_up(chunks, 128), 128, 0, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
-        else SONIC_LAUNCH(k_msm_accumulate<2>, div_up(chunks, 128), 128, 0, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
+    if (chunks && cx.opt_acc_mode == 1) {
+        const size_t smem = (size_t)ACC_SLOTS * 12 * 128 * sizeof(uint32_t);
+        static bool configured = false;
+        if (!configured) {
+            SONIC_CUDA(cudaFuncSetAttribute(k_msm_accumulate_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        SONIC_LAUNCH(k_msm_accumulate_compact, div_up(chunks, 128), 128, smem, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
+    } else if (chunks) {
+        if (cx.opt_acc_blocks == 2) SONIC_LAUNCH(k_msm_accumulate<2>, div_up(chunks, 128), 128, 0, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
+        else SONIC_LAUNCH(k_msm_accumulate<3>, div_up(chunks, 128), 128, 0, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
     }
     SONIC_CUDA(cudaEventRecord(cx.ev[9], st));
     cx.timing_ms["msm.window_bits"] = p.c;
@@ -588,7 +593,13 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const u
 
     if (cx.opt_reduce_mode == 0) {
         // flat: each thread K buckets + its offset multiple, block tree, per-job fold of the block partials
+        // buckets per thread: every thread pays ~29 extra point operations (its offset multiple and
+        // the block tree) on top of 2 per bucket, so K is as large as filling the machine allows
         uint32_t K = (uint32_t)cx.opt_reduce_k;
+        if (K == 0) {
+            const uint64_t kfill = (uint64_t)p.GB / ((uint64_t)cx.sm_count * MSM_RED_THREADS);  // about one block per SM
+            K = (uint32_t)(kfill < 8 ? 8 : (kfill > 64 ? 64 : kfill));
+        }
         if (K > p.B / MSM_RED_THREADS) K = p.B / MSM_RED_THREADS;
         if (K < 1) K = 1;
         const uint32_t S = div_up(p.B, (uint64_t)MSM_RED_THREADS * K);

@@ -41,6 +41,12 @@ void ht_fq_mulvar(int op, const uint32_t* a, const uint32_t* b, const uint32_t* 
     }
     st(out, r);
 }
+void ht_fq_mul2(const uint32_t* a1, const uint32_t* b1, const uint32_t* a2, const uint32_t* b2, uint32_t* r1, uint32_t* r2) {
+    Fq x, y;
+    fp_mul2(ld<Fq>(a1), ld<Fq>(b1), ld<Fq>(a2), ld<Fq>(b2), x, y);
+    st(r1, x);
+    st(r2, y);
+}
 void ht_fr_mulvar(int op, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* out) {
     Fr x = ld<Fr>(a), y = ld<Fr>(b), z = ld<Fr>(c), w = ld<Fr>(d), r;
     switch (op) {

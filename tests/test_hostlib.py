@@ -129,6 +129,12 @@ def test_wide_products_and_multiplier_variants(host):
             out = (ctypes.c_uint32 * (2 * n))()
             host.ht_wide_sqr(n, _arr(a, n), out)
             assert from_limbs(out) == a * a, (n, hex(a))
+    RiQ = pow(1 << 384, -1, Q)
+    for _ in range(1500):
+        a1, b1, a2, b2 = (rng.choice([0, 1, Q - 1, rng.randrange(Q)]) for _ in range(4))
+        r1, r2 = (ctypes.c_uint32 * 12)(), (ctypes.c_uint32 * 12)()
+        host.ht_fq_mul2(_arr(a1, 12), _arr(b1, 12), _arr(a2, 12), _arr(b2, 12), r1, r2)
+        assert (from_limbs(r1), from_limbs(r2)) == (a1 * b1 * RiQ % Q, a2 * b2 * RiQ % Q)
     for fn, n, p in ((host.ht_fq_mulvar, 12, Q), (host.ht_fr_mulvar, 8, R)):
         Ri = pow(1 << (32 * n), -1, p)
         edge = [0, 1, p - 1, (p - 1) // 2]
