@@ -219,10 +219,14 @@ k_msm_accumulate(const uint32_t* __restrict__ entries, const uint32_t* __restric
 // instruction cache, and `no_instruction` is its second stall reason (profiles/r01c).  Here the ten
 // multiplications of an addition run through ONE multiplier, ONE squarer and ONE fused a*b-c*d in a
 // loop (about 1 800 instructions), with the accumulator and temporaries held per thread in shared
-// memory (12 slots x 12 limbs, thread-minor so that lanes never conflict).  Exceptional cases
+// memory (9 slots x 12 limbs, thread-minor so that lanes never conflict).  Exceptional cases
 // (P = +-Q) fall back to the generic formula, which then is cold code.
-constexpr int ACC_SLOTS = 12;
-enum { SL_X1 = 0, SL_Y1, SL_ZZ1, SL_ZZZ1, SL_X2, SL_Y2, SL_P, SL_R, SL_PP, SL_PPP, SL_Q, SL_RR };
+// Nine slots (54 KB per block, four blocks per SM at 128 registers): X2, Y2 and P are dead by the
+// time PP, PPP and Q are produced, so those share their slots.  Measured on a n = 2^16 proof:
+// 12 slots / 3 blocks 42.0 ms, 9 slots / 4 blocks 40.9 ms, 7 slots (R in registers) / 5 blocks 41.0 ms.
+constexpr int ACC_SLOTS = 9;
+constexpr int ACC_COMPACT_BLOCKS = 4;
+enum { SL_X1 = 0, SL_Y1, SL_ZZ1, SL_ZZZ1, SL_X2, SL_Y2, SL_P, SL_R, SL_RR, SL_PP = SL_X2, SL_PPP = SL_Y2, SL_Q = SL_P };
 enum { OP_MULSUB = 0, OP_MUL = 1, OP_SQR = 2 };
 
 SONIC_D Fq opf_load(const uint32_t* __restrict__ f, int slot) {
@@ -236,7 +240,7 @@ SONIC_D void opf_store(uint32_t* __restrict__ f, int slot, const Fq& v) {
     for (int l = 0; l < 12; ++l) f[(slot * 12 + l) * 128] = v.l[l];
 }
 
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, ACC_COMPACT_BLOCKS)
 k_msm_accumulate_compact(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets, uint32_t GB,
                          uint32_t L, const G1Affine* __restrict__ points,
                          G1XYZZ* __restrict__ buckets, G1XYZZ* __restrict__ head, G1XYZZ* __restrict__ tail) {
