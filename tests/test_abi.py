@@ -90,3 +90,43 @@ def test_synthetic_generators_are_deterministic_and_canonical():
         assert (dot(aL, wL[q]) + dot(aR, wR[q]) + dot(aO, wO[q])) % R == cs[q]
     c = synth.synthetic_circuit_bytes(6, 3, 2)
     assert c["ints"]["cs"] == cs and bytes(c["aL"]) == synth.ints_to_bytes(aL)
+
+
+def test_product_path_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under sonic_b200/ (Python or CUDA) may import,
+    include, link or execute it, and the CUDA sources must not read the reference tree either."""
+    bad = []
+    for root, _dirs, files in os.walk(os.path.join(ROOT, "sonic_b200")):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h")):
+                continue
+            text = open(os.path.join(root, f), errors="replace").read()
+            for needle in ("import oracle", "from oracle", "oracle/", "libsonic_oracle", "/root/reference"):
+                if needle in text:
+                    bad.append((f, needle))
+    assert not bad, bad
+    # the boundary header carries no torch / C++ types
+    hdr = open(os.path.join(ROOT, "include", "sonic_b200.h")).read()
+    assert "torch" not in hdr and "std::" not in hdr and "template" not in hdr
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU restatement timed on the host cores) emits one JSON
+    line with the keys the driver reads; rank != 0 under torchrun stays silent."""
+    import json
+    import subprocess
+    import sys
+
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Mpoints/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+    env["RANK"] = "1"
+    env["WORLD_SIZE"] = "2"
+    quiet = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                           capture_output=True, text=True, env=env, timeout=300)
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""
