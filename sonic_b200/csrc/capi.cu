@@ -851,7 +851,7 @@ int sonic_set_option(const char* name, int64_t value) {
         if (value < 0 || value > 1) return fail(SONIC_ERR_INVALID_ARG, "acc_mode must be 0 or 1");
         cx.opt_acc_mode = (int)value;
     } else if (!strcmp(name, "acc_blocks")) {
-        if (value < 2 || value > 3) return fail(SONIC_ERR_INVALID_ARG, "acc_blocks must be 2 or 3");
+        if (value != 3) return fail(SONIC_ERR_INVALID_ARG, "acc_blocks is fixed at 3 in this build");
         cx.opt_acc_blocks = (int)value;
     } else if (!strcmp(name, "chunk")) {
         if (value < 0 || value > 4096) return fail(SONIC_ERR_INVALID_ARG, "chunk must be in [0, 4096]");
