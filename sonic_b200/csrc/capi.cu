@@ -844,6 +844,10 @@ int sonic_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "reduce_mode")) {
         if (value < 0 || value > 1) return fail(SONIC_ERR_INVALID_ARG, "reduce_mode must be 0 or 1");
         cx.opt_reduce_mode = (int)value;
+    } else if (!strcmp(name, "sort_mode")) {
+        // 0: thread per term + global atomics; 1: tiled counting sort, automatic tile count; 2..64: tiled, that many tiles per SM
+        if (value < 0 || value > 64) return fail(SONIC_ERR_INVALID_ARG, "sort_mode must be in [0, 64]");
+        cx.opt_sort_mode = (int)value;
     } else if (!strcmp(name, "reduce_k")) {
         if (value < 0 || value > 256) return fail(SONIC_ERR_INVALID_ARG, "reduce_k must be in [0, 256]");
         cx.opt_reduce_k = (int)value;

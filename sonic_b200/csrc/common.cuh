@@ -116,6 +116,8 @@ struct Ctx {
     int opt_acc_mode = 1;                                 // 0 straight-line mixed addition in registers, 1 compact (operand file in shared memory)
     bool opt_g2 = false;                                  // SRS.new also generates the G2 h-vectors
     int opt_reduce_mode = 0;                              // 0 flat (K buckets per thread + block tree), 1 level by level
+    int opt_sort_mode = 1;                                // 0 thread per term + global atomics, 1 tiled counting sort (shared-memory histograms)
+    bool sort_smem_set = false;
     int opt_reduce_k = 0;                                 // buckets per thread in the flat reduction (0 = automatic)
     int opt_acc_blocks = 3;                               // resident blocks/SM the accumulate kernel is compiled for (2, 3, 4)
     int opt_precompute = -1;                              // -1 auto, 0 off, else window bits

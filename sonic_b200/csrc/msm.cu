@@ -9,11 +9,18 @@
 // 148 SMs even though a single job has only 2e5-5e5 terms.
 //
 // Stages (all on one stream):
-//   1. digits+count : one thread per term recodes the scalar into W = ceil(255/c) signed
-//                     digits and histograms the global bucket ids (job, window, |digit|-1).
-//   2. scan         : exclusive prefix sum of the histogram -> bucket offsets.
-//   3. scatter      : same recode, atomic cursor per bucket -> entries sorted by bucket
-//                     (entry = point id | sign bit).
+//   1. digits+count : the terms of a job are cut into tiles, one block per tile: every term is
+//                     recoded into W = ceil(255/c) signed digits and the block histograms its
+//                     tile's bucket ids in SHARED memory (a job's whole bucket set, <= 128 KB),
+//                     then stores the histogram (tile-major: coalesced).
+//   2. scan         : per bucket, running sum over the job's tiles (each tile's slot inside the
+//                     bucket) and the bucket total; exclusive prefix sum of the totals -> bucket
+//                     offsets.
+//   3. scatter      : same recode, the block's slots come from shared-memory cursors (bucket offset
+//                     + tile slot) -> entries sorted by bucket (entry = point id | sign bit).
+//                     No global atomics at all.
+//                     (`sort_mode=0`, and bucket sets too large for shared memory: one thread per
+//                     term with global atomics on the bucket counters, the first implementation.)
 //   4. accumulate   : the hot kernel.  The sorted entry list is cut into equal chunks of L
 //                     entries, one thread per chunk, so every lane of a warp performs the
 //                     same number of mixed additions regardless of how skewed the digit
@@ -96,6 +103,95 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__
             atomicAdd(&counters[gb], 1u);
         }
     }
+}
+
+// ---- stage 1 / 3, tiled: counting sort with per-tile histograms in shared memory ---------------
+// grid = (tiles, bucket sets per job); a tile is a run of `tile_terms` consecutive terms of ONE job.
+// hist_g is tile-major: [(tile * sets + set) * B + bucket].
+// COUNT pass: hist_g receives the tile's bucket counts.  k_msm_tile_prefix then turns every count
+// into the tile's first slot inside its bucket; the SCATTER pass loads offset + slot as cursors.
+constexpr int SORT_THREADS = 1024;
+struct MsmTileTable {
+    uint32_t tile_prefix[MSM_MAX_JOBS + 1];
+    uint32_t tile_terms;
+};
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(SORT_THREADS)
+k_msm_sort_tiles(const uint32_t* __restrict__ scalars, MsmJobTable tab, MsmTileTable tt, int c, int W, uint32_t B,
+                 uint32_t level_stride,  // 0: one bucket set per window (blockIdx.y = window)
+                 uint32_t* __restrict__ hist_g, const uint32_t* __restrict__ offsets, uint32_t* __restrict__ entries) {
+    extern __shared__ uint32_t hist[];
+    const uint32_t tile = blockIdx.x, set = blockIdx.y, sets = gridDim.y;
+    int j = 0;
+    while (j + 1 < tab.M && tt.tile_prefix[j + 1] <= tile) ++j;
+    const uint32_t first = (tile - tt.tile_prefix[j]) * tt.tile_terms;
+    const uint32_t nj = tab.job[j].n;
+    const uint32_t cnt = nj - first < tt.tile_terms ? nj - first : tt.tile_terms;
+    uint32_t* g = hist_g + ((size_t)tile * sets + set) * B;
+    const uint32_t* off = SCATTER ? offsets + ((size_t)j * sets + set) * B : nullptr;
+    for (uint32_t b = threadIdx.x; b < B; b += SORT_THREADS) hist[b] = SCATTER ? g[b] + off[b] : 0u;
+    __syncthreads();
+    const uint4* sp = reinterpret_cast<const uint4*>(scalars + (size_t)(tab.job[j].scalar_off + first) * 8);
+    const uint32_t pid0 = tab.job[j].point_base + first;
+    for (uint32_t i = threadIdx.x; i < cnt; i += SORT_THREADS) {
+        const uint4 s0 = __ldg(sp + 2 * (size_t)i), s1 = __ldg(sp + 2 * (size_t)i + 1);
+        uint32_t s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) continue;
+        ScalarDigits sd(s, c);
+        const uint32_t pid = pid0 + i;
+        if (level_stride) {
+            // precomputed multiples: every window feeds the job's single bucket set, the window
+            // index selects the table level
+            for (int w = 0; w < W; ++w) {
+                const int32_t d = sd.next();
+                if (d == 0) continue;
+                const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+                const uint32_t pos = atomicAdd(&hist[mag - 1], 1u);
+                if (SCATTER) entries[pos] = (pid + (uint32_t)w * level_stride) | (d < 0 ? 0x80000000u : 0u);
+            }
+        } else {
+            int32_t d = 0;
+            for (uint32_t w = 0; w <= set; ++w) d = sd.next();  // the carry chain runs through the lower windows
+            if (d == 0) continue;
+            const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+            const uint32_t pos = atomicAdd(&hist[mag - 1], 1u);
+            if (SCATTER) entries[pos] = pid | (d < 0 ? 0x80000000u : 0u);
+        }
+    }
+    if (!SCATTER) {
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < B; b += SORT_THREADS) g[b] = hist[b];
+    }
+}
+
+// thread per global bucket: counts of the job's tiles -> each tile's first slot inside the bucket
+// (in place), and the bucket's total.  Consecutive threads read consecutive words of every tile.
+__global__ void __launch_bounds__(256)
+k_msm_tile_prefix(uint32_t* __restrict__ hist_g, MsmTileTable tt, uint32_t per_job /* sets * B */, uint32_t GB,
+                  uint32_t* __restrict__ counts) {
+    const uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gb > GB) return;
+    if (gb == GB) { counts[gb] = 0; return; }
+    const uint32_t j = gb / per_job, within = gb - j * per_job;
+    const uint32_t t0 = tt.tile_prefix[j], t1 = tt.tile_prefix[j + 1];
+    uint32_t* h = hist_g + (size_t)t0 * per_job + within;
+    uint32_t run = 0;
+    uint32_t t = t0;
+    for (; t + 4 <= t1; t += 4, h += 4 * (size_t)per_job) {
+        const uint32_t v0 = h[0], v1 = h[per_job], v2 = h[2 * (size_t)per_job], v3 = h[3 * (size_t)per_job];
+        h[0] = run;
+        h[per_job] = run + v0;
+        h[2 * (size_t)per_job] = run + v0 + v1;
+        h[3 * (size_t)per_job] = run + v0 + v1 + v2;
+        run += v0 + v1 + v2 + v3;
+    }
+    for (; t < t1; ++t, h += per_job) {
+        const uint32_t v = *h;
+        *h = run;
+        run += v;
+    }
+    counts[gb] = run;
 }
 
 // ---- stage 2: exclusive scan of u32 (three-kernel, 4096 items per block) ------------------
@@ -371,16 +467,46 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const u
 
     SONIC_CUDA(cudaEventRecord(cx.ev[0], st));
     uint32_t* offsets = ar.get<uint32_t>((size_t)p.GB + 1);
-    uint32_t* cursors = ar.get<uint32_t>((size_t)p.GB + 1);
-    SONIC_CUDA(cudaMemsetAsync(offsets, 0, ((size_t)p.GB + 1) * 4, st));
-    if (n_tot) SONIC_LAUNCH(k_msm_digits<false>, div_up(n_tot, 256), 256, 0, d_scalars, tab, n_tot, p.c, p.W, p.B, level_stride, offsets, (uint32_t*)nullptr);
-    exclusive_scan_u32(ar, offsets, offsets, p.GB + 1);
-    SONIC_CUDA(cudaMemcpyAsync(cursors, offsets, ((size_t)p.GB + 1) * 4, cudaMemcpyDeviceToDevice, st));
     // zero digits are not stored, so n_tot*W is only an upper bound of the entry count; the
     // accumulate grid is sized for the bound and reads the true count from offsets[GB]
     const uint64_t total_max = (uint64_t)n_tot * p.W;
     uint32_t* entries = ar.get<uint32_t>(total_max ? total_max : 1);
-    if (n_tot) SONIC_LAUNCH(k_msm_digits<true>, div_up(n_tot, 256), 256, 0, d_scalars, tab, n_tot, p.c, p.W, p.B, level_stride, cursors, entries);
+    // Tiles never cross a job border.  Blocks start in index order, so the tiles in flight belong to
+    // a few consecutive jobs; with many small tiles per job (about ten per SM in total) the slice of
+    // the entry array being scattered into at any moment (those jobs' entries) stays inside L2 and
+    // the 4-byte stores merge into whole sectors before they reach HBM.  With two tiles per SM the
+    // scatter moved 5.7 GB through DRAM for 0.48 GB of entries (profiles/r01e).
+    MsmTileTable tt;
+    memset(&tt, 0, sizeof tt);
+    const uint32_t target_tiles = (uint32_t)cx.sm_count * (cx.opt_sort_mode >= 2 ? (uint32_t)cx.opt_sort_mode : 10u);
+    tt.tile_terms = div_up(n_tot ? n_tot : 1, target_tiles > (uint32_t)M ? target_tiles - (uint32_t)M : 1);
+    if (tt.tile_terms < 2048) tt.tile_terms = 2048;
+    for (int i = 0; i < M; ++i) tt.tile_prefix[i + 1] = tt.tile_prefix[i] + div_up(jobs[i].n, tt.tile_terms);
+    const uint32_t tiles = tt.tile_prefix[M];
+    const uint64_t hist_len = (uint64_t)tiles * p.sets * p.B;
+    const size_t sort_smem = (size_t)p.B * sizeof(uint32_t);
+    const bool tiled = cx.opt_sort_mode != 0 && n_tot > 0 && sort_smem <= (size_t(128) << 10) && hist_len <= (1ull << 26);  // <= 256 MB of histograms
+    cx.timing_ms["msm.sort_tiles"] = tiled ? tiles : 0;
+    if (tiled) {
+        if (!cx.sort_smem_set) {
+            SONIC_CUDA(cudaFuncSetAttribute(k_msm_sort_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10));
+            SONIC_CUDA(cudaFuncSetAttribute(k_msm_sort_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10));
+            cx.sort_smem_set = true;
+        }
+        uint32_t* hist = ar.get<uint32_t>(hist_len);
+        const dim3 grid(tiles, (unsigned)p.sets);
+        SONIC_LAUNCH(k_msm_sort_tiles<false>, grid, SORT_THREADS, sort_smem, d_scalars, tab, tt, p.c, p.W, p.B, level_stride, hist, (const uint32_t*)nullptr, (uint32_t*)nullptr);
+        SONIC_LAUNCH(k_msm_tile_prefix, div_up((uint64_t)p.GB + 1, 256), 256, 0, hist, tt, (uint32_t)p.sets * p.B, p.GB, offsets);
+        exclusive_scan_u32(ar, offsets, offsets, p.GB + 1);
+        SONIC_LAUNCH(k_msm_sort_tiles<true>, grid, SORT_THREADS, sort_smem, d_scalars, tab, tt, p.c, p.W, p.B, level_stride, hist, offsets, entries);
+    } else {
+        uint32_t* cursors = ar.get<uint32_t>((size_t)p.GB + 1);
+        SONIC_CUDA(cudaMemsetAsync(offsets, 0, ((size_t)p.GB + 1) * 4, st));
+        if (n_tot) SONIC_LAUNCH(k_msm_digits<false>, div_up(n_tot, 256), 256, 0, d_scalars, tab, n_tot, p.c, p.W, p.B, level_stride, offsets, (uint32_t*)nullptr);
+        exclusive_scan_u32(ar, offsets, offsets, p.GB + 1);
+        SONIC_CUDA(cudaMemcpyAsync(cursors, offsets, ((size_t)p.GB + 1) * 4, cudaMemcpyDeviceToDevice, st));
+        if (n_tot) SONIC_LAUNCH(k_msm_digits<true>, div_up(n_tot, 256), 256, 0, d_scalars, tab, n_tot, p.c, p.W, p.B, level_stride, cursors, entries);
+    }
     SONIC_CUDA(cudaEventRecord(cx.ev[1], st));
 
     const uint32_t chunks = div_up(total_max, p.L);

@@ -130,6 +130,38 @@ def test_msm_sizes_and_windows_vs_trapdoor(gpu):
         gpu.set_option("chunk", 0)
 
 
+def test_msm_sort_paths_agree(gpu):
+    """The tiled counting sort (shared-memory histograms, several tiles per job, one bucket set per
+    window or one per job with the precomputed tables) and the first implementation (thread per
+    term, global atomics) feed the same buckets: same element, and the trapdoor identity holds."""
+    rng = random.Random(21)
+    d = 3500
+    x = rng.randrange(1, R)
+    xi = pow(x, -1, R)
+    N = 7000                                  # > 3 tiles of 2048 terms
+    pool = [0, 1, R - 1, rng.randrange(R)]
+    sc = [rng.randrange(R) if k % 3 else rng.choice(pool) for k in range(N)]
+    lo = -(N // 2)
+    acc = sum(v * (pow(x, lo + k, R) if lo + k >= 0 else pow(xi, -(lo + k), R)) for k, v in enumerate(sc)) % R
+    want = C(bls.g1_mul_gen(acc))
+    try:
+        for pre in (0, -1):
+            gpu.set_option("precompute", pre)
+            g = gpu.SRS.new(d, x, 4)
+            for wb in ((0, 5, 12, 16) if pre == 0 else (0,)):
+                gpu.set_option("window_bits", wb)
+                for mode in (0, 1):
+                    gpu.set_option("sort_mode", mode)
+                    assert gpu.msm(g, 0, lo, sc) == want, (pre, wb, mode)
+                    tiles = gpu.last_timing_ms("msm.sort_tiles")
+                    assert (tiles >= 4) if mode == 1 else (tiles == 0), (pre, wb, mode, tiles)
+            g.free()
+    finally:
+        gpu.set_option("precompute", -1)
+        gpu.set_option("window_bits", 0)
+        gpu.set_option("sort_mode", 1)
+
+
 def test_msm_skewed_and_degenerate(gpu):
     """Zeros, +-1 and repeated scalars (heavy buckets), and x = 1 where every base coincides."""
     rng = random.Random(15)
