@@ -1,5 +1,5 @@
-// Shared pieces of the two bucket-accumulation kernels (each lives in its own translation unit so
-// that ptxas works on them in parallel: they are the largest kernels of the library).
+// Shared pieces of the MSM translation units (sort + orchestration in msm.cu, the two bucket-accumulation
+// kernels and the reduction stages each in their own, so that ptxas works on the large kernels in parallel).
 #pragma once
 #include "internal.h"
 #include "g1io.cuh"
@@ -13,10 +13,19 @@ SONIC_D G1Affine fetch_entry(const G1Affine* __restrict__ points, uint32_t e) {
     return p;
 }
 
+struct MsmPlan {
+    int c, W, sets;
+    uint32_t B, GB, L, n_tot;
+};
+
 // launchers (msm_acc_regs.cu, msm_acc_compact.cu)
 void launch_accumulate_regs(Ctx& cx, uint32_t chunks, const uint32_t* entries, const uint32_t* offsets, uint32_t GB, uint32_t L,
                             const G1Affine* points, G1XYZZ* buckets, G1XYZZ* head, G1XYZZ* tail);
 void launch_accumulate_compact(Ctx& cx, uint32_t chunks, const uint32_t* entries, const uint32_t* offsets, uint32_t GB, uint32_t L,
                                const G1Affine* points, G1XYZZ* buckets, G1XYZZ* head, G1XYZZ* tail);
+
+// stages 5-7 (msm_reduce.cu)
+void msm_reduce_stage(Ctx& cx, const MsmPlan& p, int M, const uint32_t* offsets, uint32_t chunks, G1XYZZ* buckets,
+                      const G1XYZZ* head, const G1XYZZ* tail, G1Affine* d_out_aff, uint8_t* d_out_comp);
 
 }  // namespace sonic
