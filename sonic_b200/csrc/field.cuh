@@ -593,6 +593,95 @@ SONIC_HD Fp<P> fp_inv(const Fp<P>& a) {
     return fp_pow_limbs(a, e, P::N);
 }
 
+// Inverse of ONE element on ONE thread without the Fermat ladder: Kaliski's almost-inverse (binary
+// extended Euclid on the limbs -- shifts, additions, subtractions; k <= 2*bits iterations) yields
+// a^-1 * 2^k, then four Montgomery products remove the power of two and restore the Montgomery
+// factor.  The dependent chain is about 8x shorter than 2*bits field multiplications, which is what
+// the end of an MSM pays for (to-affine of a single point on a single thread).  Data-dependent
+// branches: not for warps of independent inversions (use fp_inv there).  inv(0) = 0.
+template <class P>
+SONIC_HD Fp<P> fp_inv_euclid(const Fp<P>& a) {
+    constexpr int N = P::N;
+    if (a.is_zero()) return a;
+    uint32_t u[N], v[N], r[N], s[N], t[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { u[i] = P::P(i); v[i] = a.l[i]; r[i] = 0; s[i] = 0; }
+    s[0] = 1;
+    int k = 0;
+    for (;;) {
+        uint32_t vz = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) vz |= v[i];
+        if (vz == 0) break;
+        if ((u[0] & 1u) == 0) {
+#pragma unroll
+            for (int i = 0; i < N - 1; ++i) u[i] = (u[i] >> 1) | (u[i + 1] << 31);
+            u[N - 1] >>= 1;
+#pragma unroll
+            for (int i = N - 1; i > 0; --i) s[i] = (s[i] << 1) | (s[i - 1] >> 31);
+            s[0] <<= 1;
+        } else if ((v[0] & 1u) == 0) {
+#pragma unroll
+            for (int i = 0; i < N - 1; ++i) v[i] = (v[i] >> 1) | (v[i + 1] << 31);
+            v[N - 1] >>= 1;
+#pragma unroll
+            for (int i = N - 1; i > 0; --i) r[i] = (r[i] << 1) | (r[i - 1] >> 31);
+            r[0] <<= 1;
+        } else {
+            t[0] = Chain::sub_cc(u[0], v[0]);
+#pragma unroll
+            for (int i = 1; i < N; ++i) t[i] = Chain::subc_cc(u[i], v[i]);
+            const uint32_t borrow = Chain::subc(0, 0);  // 0xffffffff if u < v
+            uint32_t tz = 0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) tz |= t[i];
+            if (borrow == 0 && tz != 0) {
+                // u > v: u = (u - v) / 2, r += s, s *= 2
+#pragma unroll
+                for (int i = 0; i < N - 1; ++i) u[i] = (t[i] >> 1) | (t[i + 1] << 31);
+                u[N - 1] = t[N - 1] >> 1;
+                r[0] = Chain::add_cc(r[0], s[0]);
+#pragma unroll
+                for (int i = 1; i < N; ++i) r[i] = Chain::addc_cc(r[i], s[i]);
+#pragma unroll
+                for (int i = N - 1; i > 0; --i) s[i] = (s[i] << 1) | (s[i - 1] >> 31);
+                s[0] <<= 1;
+            } else {
+                // v >= u: v = (v - u) / 2, s += r, r *= 2
+                t[0] = Chain::sub_cc(v[0], u[0]);
+#pragma unroll
+                for (int i = 1; i < N; ++i) t[i] = Chain::subc_cc(v[i], u[i]);
+#pragma unroll
+                for (int i = 0; i < N - 1; ++i) v[i] = (t[i] >> 1) | (t[i + 1] << 31);
+                v[N - 1] = t[N - 1] >> 1;
+                s[0] = Chain::add_cc(s[0], r[0]);
+#pragma unroll
+                for (int i = 1; i < N; ++i) s[i] = Chain::addc_cc(s[i], r[i]);
+#pragma unroll
+                for (int i = N - 1; i > 0; --i) r[i] = (r[i] << 1) | (r[i - 1] >> 31);
+                r[0] <<= 1;
+            }
+        }
+        ++k;
+    }
+    // r < 2p holds a^-1 * 2^k up to sign: x = p - (r mod p)
+    Fp<P> x;
+#pragma unroll
+    for (int i = 0; i < N; ++i) x.l[i] = r[i];
+    fp_reduce_once(x);
+    x = fp_neg(x);
+    // input a = A*R (Montgomery form), so x = A^-1 R^-1 2^k; wanted A^-1 R = x * R^2 / 2^k.
+    // Two products by R^2 add R each; a product by 2^j divides by 2^(32N - j): two of them remove 2^k.
+    x = fp_mul(fp_mul(x, Fp<P>::r2()), Fp<P>::r2());
+    const int d1 = k >> 1, d2 = k - d1;
+    Fp<P> w = Fp<P>::zero();
+    w.l[(32 * N - d1) >> 5] = 1u << ((32 * N - d1) & 31);
+    x = fp_mul(x, w);
+    w = Fp<P>::zero();
+    w.l[(32 * N - d2) >> 5] = 1u << ((32 * N - d2) & 31);
+    return fp_mul(x, w);
+}
+
 // a^k for a 64-bit non-negative exponent
 template <class P>
 SONIC_HD Fp<P> fp_pow_u64(const Fp<P>& a, uint64_t k) {

@@ -174,6 +174,18 @@ SONIC_HD G1Affine g1_to_affine(const G1XYZZ& p) {
     return r;
 }
 
+// the same for one point on one thread (the end of an MSM): binary-Euclid inverse
+SONIC_HD G1Affine g1_to_affine_single(const G1XYZZ& p) {
+    if (p.is_inf()) return G1Affine::inf();
+    Fq zi = fp_inv_euclid(p.zzz);
+    Fq t = fp_mul(p.zz, zi);
+    Fq zzi = fp_sqr(t);
+    G1Affine r;
+    r.x = fp_mul(p.x, zzi);
+    r.y = fp_mul(p.y, zi);
+    return r;
+}
+
 // k * p for a small unsigned multiplier (double-and-add, MSB first)
 SONIC_HD G1XYZZ g1_mul_small(const G1XYZZ& p, uint32_t k) {
     G1XYZZ r = G1XYZZ::inf();

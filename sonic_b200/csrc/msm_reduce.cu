@@ -182,7 +182,7 @@ k_msm_finish(const G1XYZZ* __restrict__ partial, uint32_t S, int W, int c, G1Aff
                 g1_add(acc, win[w]);
             }
         }
-        G1Affine a = g1_to_affine(acc);
+        G1Affine a = g1_to_affine_single(acc);
         if (out_aff) out_aff[job] = a;
         if (out_comp) g1_compress(a, out_comp + (size_t)job * 48);
     }

@@ -18,6 +18,7 @@ __global__ void k_selftest_field(int op, const F* __restrict__ a, const F* __res
         case 4: r = fp_from_mont(x); break;
         case 5: r = fp_inv(x); break;
         case 6: r = fp_sqr(x); break;
+        case 8: r = fp_inv_euclid(x); break;
         default: r = fp_neg(x); break;
     }
     out[i] = r;

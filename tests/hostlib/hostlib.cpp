@@ -12,7 +12,7 @@ template <class F> static F ld(const uint32_t* p) { F r; memcpy(r.l, p, sizeof(r
 template <class F> static void st(uint32_t* p, const F& v) { memcpy(p, v.l, sizeof(v.l)); }
 
 extern "C" {
-// op: 0 mul, 1 add, 2 sub, 3 to_mont(a), 4 from_mont(a), 5 inv(a), 6 sqr(a), 7 neg(a)
+// op: 0 mul, 1 add, 2 sub, 3 to_mont(a), 4 from_mont(a), 5 inv(a), 6 sqr(a), 7 neg(a), 8 inv(a) by binary Euclid
 void ht_fq_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     Fq x = ld<Fq>(a), y = ld<Fq>(b), r;
     switch (op) {
@@ -23,6 +23,7 @@ void ht_fq_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
         case 4: r = fp_from_mont(x); break;
         case 5: r = fp_inv(x); break;
         case 6: r = fp_sqr(x); break;
+        case 8: r = fp_inv_euclid(x); break;
         default: r = fp_neg(x); break;
     }
     st(out, r);
@@ -83,6 +84,7 @@ void ht_fr_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
         case 4: r = fp_from_mont(x); break;
         case 5: r = fp_inv(x); break;
         case 6: r = fp_sqr(x); break;
+        case 8: r = fp_inv_euclid(x); break;
         default: r = fp_neg(x); break;
     }
     st(out, r);

@@ -44,6 +44,9 @@ def test_field_ops_bit_exact(gpu, field):
     got = _run_field(gpu, field, 5, small, small)
     want = [0 if x == 0 else pow(x * Ri % p, -1, p) * Rm % p for x in small]
     assert got == want
+    # the single-thread inverse used by the MSM's final to-affine (binary Euclid, divergent lanes here)
+    small = a[:81] + a[-200:]
+    assert _run_field(gpu, field, 8, small, small) == [0 if x == 0 else pow(x * Ri % p, -1, p) * Rm % p for x in small]
 
 
 def _xyzz(P, z=1):

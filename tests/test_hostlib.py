@@ -54,6 +54,10 @@ def test_montgomery_field_ops(host, field):
     for _ in range(10):
         a = rng.randrange(1, p)
         assert op(5, a * Rm % p) == pow(a, -1, p) * Rm % p
+    # binary-Euclid inverse (the MSM's final to-affine): edge values and random ones
+    assert op(8, 0) == 0
+    for a in [1, 2, 3, p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, Rm % p, Ri, 1 << 31, 1 << 32, (1 << (p.bit_length() - 1))] + [rng.randrange(1, p) for _ in range(400)]:
+        assert op(8, a * Rm % p) == pow(a, -1, p) * Rm % p, a
 
 
 def test_g1_formulas_all_cases(host):
