@@ -168,6 +168,7 @@ def main() -> None:
     ap.add_argument("--no-sweep", action="store_true", help="skip the standalone MSM sweep (config 3)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--sweep-max", type=int, default=24)
+    ap.add_argument("--sweep-tables", type=int, default=1, help="1: precomputed 20-bit window tables for the large sweep SRS (42 GB at d=2^23); 0: none")
     ap.add_argument("--config5", action="store_true", help="also run BASELINE config 5: SRS.new d=2^22, then 64 proofs at n=2^14 spread over the ranks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -324,6 +325,14 @@ def main() -> None:
     ev_ms, wall_ms, launches, proof = timed(step_resident, args.steps)
     stage = {k: sb.last_timing_ms(k) for k in ("msm", "msm.sort", "msm.accumulate", "msm.accumulate_kernel", "msm.reduce", "poly", "total",
                                                "msm.window_bits", "msm.windows", "msm.terms", "msm.entries", "msm.chunk", "msm.buckets")}
+    per_rank = None
+    if world > 1:
+        # every rank's view of the last timed step (device ms), to see the balance of the dealing
+        keys = ("total", "poly", "msm.sort", "msm.accumulate", "msm.reduce", "msm.terms", "msm.jobs")
+        mine = torch.tensor([stage[k] if k in stage else sb.last_timing_ms(k) for k in keys], dtype=torch.float64, device="cuda")
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {k: [round(float(t[i]), 3) for t in allr] for i, k in enumerate(keys)}
     e2e_ev_ms, e2e_wall_ms, _, proof2 = timed(step_e2e, args.steps)
     clocks = sampler.stop()
     if proof != proof2 or proof != p_res:
@@ -376,7 +385,12 @@ def main() -> None:
         small_d = 1 << 19
         small = srs if small_d <= d else sb.SRS.new(small_d, x, alpha)
         dd = 1 << (top - 1)
+        # the large SRS gets 20-bit window tables (13 levels, 42 GB at d = 2^23, one-time cost in SRS.new):
+        # 13 insertions per point into ONE set of 2^19 buckets instead of 13-15 sets and a Horner tail
+        if dd > small_d:
+            sb.set_option("precompute", 20 if args.sweep_tables else 0)
         big = small if dd <= small_d else sb.SRS.new(dd, x, alpha)
+        sb.set_option("precompute", -1)
         for logn in range(16, top + 1, 2):
             N = 1 << logn
             for kind in ("uniform", "skewed"):
@@ -493,6 +507,7 @@ def main() -> None:
             "shard_phases_ms_rank0": None if world == 1 or not phase["calls"] else {
                 "shard_call": 1e3 * phase["shard"] / max(1, args.steps), "exchange": 1e3 * phase["exchange"] / phase["calls"],
                 "combine": 1e3 * phase["combine"] / phase["calls"], "note": "host wall clock on rank 0 over the timed steps (exchange/combine: both timed regions)"},
+            "shard_stages_ms_per_rank": per_rank,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "msm_sweep": sweep,
