@@ -199,15 +199,15 @@ __global__ void __launch_bounds__(256) k_build_suy_dot_csr(SparseView L, SparseV
 // rnd_m: 2M+8 draws (Montgomery), M = number of (y_j, z_j) pairs.  Layout of pts: y, z, yz, y_1..y_M, z_1..z_M, u, v
 __global__ void k_prove_points(const Fr* __restrict__ rnd_m, uint32_t M, int has_main, Fr* __restrict__ pts) {
     const uint32_t np = 2 * M + 5;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= np) return;
+    const uint32_t t = blockIdx.x;   // one single-thread block per point: the Euclid inverse branches on the data
+    if (t >= np || threadIdx.x != 0) return;
     Fr v;
     if (t == 0) v = has_main ? rnd_m[4] : Fr::one();
     else if (t == 1) v = has_main ? rnd_m[5] : Fr::one();
     else if (t == 2) v = has_main ? fp_mul(rnd_m[4], rnd_m[5]) : Fr::one();
     else v = rnd_m[6 + (t - 3)];  // ys, zs, u, v are contiguous in the draw order
     pts[t] = v;
-    pts[np + t] = fp_inv(v);
+    pts[np + t] = fp_inv_euclid(v);
 }
 
 // first index in [a, b) (relative to s) whose scalar is non-zero -> atomicMin into *out
@@ -524,7 +524,7 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
     enum { PT_Y = 0, PT_Z = 1, PT_YZ = 2, PT_YJ = 3 };
     const uint32_t PT_ZJ = 3 + M, PT_U = 3 + 2 * M, PT_V = 4 + 2 * M;
     Fr* pts = ar.get<Fr>(2 * np);
-    SONIC_LAUNCH(k_prove_points, div_up(np, 32), 32, 0, rnd_m, M, has_main ? 1 : 0, pts);
+    SONIC_LAUNCH(k_prove_points, np, 32, 0, rnd_m, M, has_main ? 1 : 0, pts);
     const uint64_t tl = std::max<uint64_t>(3 * (uint64_t)n + 8, 2 * (uint64_t)n + Q + 4);
     Fr* tabs = ar.get<Fr>(2 * (size_t)np * tl);
     pow_tables(cx, pts, 2 * np, tabs, tl, tl);
