@@ -431,11 +431,12 @@ __global__ void k_points_to_raw(const G1Affine* __restrict__ pts, uint32_t n, Fq
 }
 
 // out48[m] = compress(sum_r raw[r][m]),  raw laid out [world][nm] x 96 B.  When at most one rank
-// contributes (whole MSMs dealt to ranks: everybody else holds the identity) the point is already
-// affine and is only re-encoded: no addition, no second inversion.
+// contributes (an MSM owned whole by one rank: everybody else holds the identity) the point is
+// already affine and is only re-encoded: no addition, no second inversion.  At most world-1 MSMs
+// are split between ranks and take the addition path.
 __global__ void k_fold_partials(const Fq* __restrict__ raw, uint32_t nm, uint32_t world, uint8_t* __restrict__ out48) {
-    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= nm) return;
+    const uint32_t m = blockIdx.x;   // one single-thread block per MSM: the Euclid inverse branches on the data
+    if (m >= nm || threadIdx.x != 0) return;
     uint32_t contributors = 0;
     G1Affine only = G1Affine::inf();
     for (uint32_t r = 0; r < world; ++r) {
@@ -459,11 +460,11 @@ __global__ void k_fold_partials(const Fq* __restrict__ raw, uint32_t nm, uint32_
         a.y = fp_to_mont(p[1]);
         g1_madd(acc, a);  // (0,0) marks infinity and is skipped
     }
-    g1_compress(g1_to_affine(acc), out48 + (size_t)m * 48);
+    g1_compress(g1_to_affine_single(acc), out48 + (size_t)m * 48);
 }
 
-// Sharded proofs: every rank runs the Fr side in full and the slice [rank/world, (rank+1)/world)
-// of every MSM; its output is then a "shard blob" = nm raw partial sums (96 B) followed by the
+// Sharded proofs: every rank runs the Fr side in full and its equal run of the proof's MSM terms
+// (see prove_run); its output is then a "shard blob" = nm raw partial sums (96 B) followed by the
 // nF field values (32 B) in record order.  prove_combine folds the gathered blobs.
 int prove_combine(Ctx& cx, uint32_t M, bool has_main, uint32_t world, const uint8_t* blobs, uint8_t* out,
                   uint64_t cap, uint64_t* written, const void* d_gathered) {
@@ -484,7 +485,7 @@ int prove_combine(Ctx& cx, uint32_t M, bool has_main, uint32_t world, const uint
     for (uint32_t r = 0; r < world && !d_gathered; ++r)
         SONIC_CUDA(cudaMemcpyAsync(d_raw + 2 * (size_t)r * nm, blobs + r * blob, (size_t)nm * 96, cudaMemcpyHostToDevice, cx.stream));
     uint8_t* d_out = cx.arena.get<uint8_t>((size_t)nm * 48);
-    SONIC_LAUNCH(k_fold_partials, div_up(nm, 32), 32, 0, d_raw_c, nm, world, d_out);
+    SONIC_LAUNCH(k_fold_partials, nm, 32, 0, d_raw_c, nm, world, d_out);
     std::vector<uint8_t> g48((size_t)nm * 48);
     SONIC_CUDA(cudaMemcpyAsync(g48.data(), d_out, g48.size(), cudaMemcpyDeviceToHost, cx.stream));
     SONIC_CUDA(cudaStreamSynchronize(cx.stream));
@@ -679,29 +680,24 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
     SONIC_CUDA(cudaMemsetAsync(viol, 0xff, 12 * (size_t)nm, st));
     std::vector<MsmJob> jobs(nm);
     std::vector<int64_t> slice_lo(nm, 0);
-    // Sharding over `world` ranks, two ways: whole MSMs are dealt to the ranks
-    // (longest first, to the least loaded rank) when that balances, so that sorting, bucket
-    // reduction and the tail shrink with the rank count too; otherwise every MSM is cut into
-    // `world` contiguous slices.  Both are deterministic functions of the sizes: all ranks agree.
-    std::vector<int> owner(nm, -1);
-    bool by_job = false;
+    // Sharding over `world` ranks: the (clipped) exponent windows of all MSMs,
+    // concatenated in record order, are cut into `world` equal runs of terms.  A rank so owns a few
+    // whole MSMs plus at most two partial ones -- sorting, bucket reduction and the tail shrink with
+    // the rank count, the loads differ by at most one term, and at most world-1 MSMs are split (their
+    // partial sums meet in the fold).  A deterministic function of the sizes: all ranks agree.
+    // Mirrored by sonic_b200/dist.py:deal_terms.
+    uint64_t run_lo = 0, run_hi = 0;
     if (sharded) {
-        std::vector<uint64_t> load(world, 0);
-        std::vector<uint32_t> order(nm);
-        for (uint32_t i = 0; i < nm; ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return pm[a].len > pm[b].len; });
         uint64_t total_len = 0;
-        for (uint32_t i : order) {
-            uint32_t best = 0;
-            for (uint32_t r = 1; r < world; ++r) if (load[r] < load[best]) best = r;
-            owner[i] = (int)best;
-            load[best] += pm[i].len;
-            total_len += pm[i].len;
+        for (uint32_t i = 0; i < nm; ++i) {
+            const int64_t lo = pm[i].lo, hi = pm[i].lo + (int64_t)pm[i].len;
+            const int64_t clo = std::max(lo, -d), chi = std::max(clo, std::min(hi, d + 1));
+            total_len += (uint64_t)(chi - clo);
         }
-        uint64_t max_load = 0;
-        for (uint64_t l : load) max_load = std::max(max_load, l);
-        by_job = nm >= world && max_load * world <= total_len + total_len / 5;  // within 20% of perfect balance
+        run_lo = total_len * rank / world;
+        run_hi = total_len * (rank + 1) / world;
     }
+    uint64_t run_pos = 0;
     struct Rng { int64_t a, b; };
     std::vector<Rng> rngs(3 * (size_t)nm, Rng{0, 0});
     for (uint32_t i = 0; i < nm; ++i) {
@@ -718,13 +714,13 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
             }
         }
         int64_t clo = std::max(lo, -d), chi = std::max(clo, std::min(hi, d + 1));
-        if (sharded && by_job) {
-            if (owner[i] != (int)rank) chi = clo;  // another rank's MSM
-        } else if (sharded) {  // this rank's contiguous slice of the exponent window
-            const int64_t span = chi - clo;
-            const int64_t a = clo + span * (int64_t)rank / (int64_t)world, b = clo + span * (int64_t)(rank + 1) / (int64_t)world;
-            clo = a;
-            chi = b;
+        if (sharded) {  // the part of this window inside the rank's run of terms (often all or nothing)
+            const uint64_t span = (uint64_t)(chi - clo);
+            const uint64_t a = run_lo > run_pos ? std::min(run_lo - run_pos, span) : 0;
+            const uint64_t b = run_hi > run_pos ? std::min(run_hi - run_pos, span) : 0;
+            run_pos += span;
+            chi = clo + (int64_t)b;
+            clo = clo + (int64_t)a;
         }
         slice_lo[i] = clo;
         jobs[i].point_base = (uint32_t)srs->index(m.family, clo);
@@ -740,11 +736,11 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
         jobs[i].scalar_off = (uint32_t)((pm[i].scal - sbase) + (slice_lo[i] - pm[i].lo));
     G1Affine* d_aff = ar.get<G1Affine>(nm);
     uint8_t* d_comp = ar.get<uint8_t>((size_t)nm * 48);
-    if (sharded && by_job) {
-        // only this rank's MSMs enter the pipeline; the others contribute the identity
+    if (sharded) {
+        // only this rank's MSMs (whole or partial) enter the pipeline; the others contribute the identity
         SONIC_CUDA(cudaMemsetAsync(d_aff, 0, (size_t)nm * sizeof(G1Affine), st));
         std::vector<uint32_t> mine;
-        for (uint32_t i = 0; i < nm; ++i) if (owner[i] == (int)rank) mine.push_back(i);
+        for (uint32_t i = 0; i < nm; ++i) if (jobs[i].n > 0) mine.push_back(i);
         G1Affine* d_mine = ar.get<G1Affine>(mine.size() ? mine.size() : 1);
         for (size_t first = 0; first < mine.size(); first += MSM_MAX_JOBS) {
             const size_t cnt = std::min<size_t>(MSM_MAX_JOBS, mine.size() - first);

@@ -1,7 +1,8 @@
 """Multi-GPU plumbing: one process per GPU, torch.distributed for the exchange.
 
 The path shards two ways: across independent proofs (no exchange at all)
-and, for one proof, across contiguous slices of every MSM.  The second has exactly one
+and, for one proof, across equal runs of the proof's MSM terms (`deal_terms`; a standalone MSM is
+cut into contiguous slices, `slice_bounds`).  The second has exactly one
 exchange step: each rank ends with 4Q+7 partial G1 sums (96 B each) plus the field values;
 one all-gather of that small blob (NCCL over NVLink on GPUs, gloo in the CPU tests) and a
 fold with `<>` complete the proof.  Nothing else crosses ranks: the SRS is replicated.
@@ -15,26 +16,29 @@ import torch.distributed as dist
 
 
 def slice_bounds(lo: int, hi: int, rank: int, world: int) -> Tuple[int, int]:
-    """The contiguous part [a, b) of an exponent window [lo, hi) that `rank` of `world` sums
-    (same arithmetic as prove_run in csrc/prove.cu)."""
+    """The contiguous part [a, b) of an exponent window [lo, hi) that `rank` of `world` sums in a
+    standalone sharded MSM."""
     span = hi - lo
     return lo + span * rank // world, lo + span * (rank + 1) // world
 
 
-def deal_jobs(lengths: Sequence[int], world: int):
-    """How prove_run (csrc/prove.cu) deals whole MSMs to ranks: longest first, each to the least
-    loaded rank.  Returns (owner per job, by_job) where by_job says whether that assignment is
-    within 20% of perfect balance; otherwise every MSM is sliced with `slice_bounds` instead."""
-    order = sorted(range(len(lengths)), key=lambda i: -lengths[i])  # stable: ties keep record order
-    load = [0] * world
-    owner = [-1] * len(lengths)
-    for i in order:
-        r = min(range(world), key=lambda k: load[k])
-        owner[i] = r
-        load[r] += lengths[i]
+def deal_terms(lengths: Sequence[int], world: int) -> List[List[Tuple[int, int]]]:
+    """How prove_run (csrc/prove.cu) shards one proof: the (clipped) exponent windows of all MSMs,
+    concatenated in record order, are cut into `world` equal runs of terms.  Returns, per rank, the
+    part [a, b) of every MSM's window (offsets into the window; a == b where the rank holds nothing).
+    A rank owns a few whole MSMs and at most two partial ones; at most world-1 MSMs are split."""
     total = sum(lengths)
-    by_job = len(lengths) >= world and max(load) * world <= total + total // 5
-    return owner, by_job
+    out = []
+    for rank in range(world):
+        lo, hi = total * rank // world, total * (rank + 1) // world
+        pos, parts = 0, []
+        for n in lengths:
+            a = min(max(lo - pos, 0), n)
+            b = min(max(hi - pos, 0), n)
+            parts.append((a, b))
+            pos += n
+        out.append(parts)
+    return out
 
 
 def all_gather_bytes(blob: bytes, group=None) -> List[bytes]:

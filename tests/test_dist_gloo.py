@@ -1,5 +1,5 @@
-"""CPU, world_size 2, gloo: the multi-GPU path's host logic -- slicing of every MSM across
-ranks, the all-gather of the shard blobs (sonic_b200/dist.py) and the fold -- with the oracle
+"""CPU, world_size 2, gloo: the multi-GPU path's host logic -- dealing equal runs of the proof's
+MSM terms to the ranks, the all-gather of the shard blobs (sonic_b200/dist.py) and the fold -- with the oracle
 standing in for the CUDA kernels.  The sharded proof must equal the single-rank proof."""
 import os
 import random
@@ -42,10 +42,10 @@ def _worker(rank, world, port, result_dir):
     assert len(msms) == 4 * Q + 7 and len(fvals) == 2 * Q + 5
     # this rank's shard blob: raw partial sums over its slice of every MSM, then the Fr values
     parts = []
-    for alpha, lo, scal in msms:
-        clo, chi = max(lo, -d), min(lo + len(scal), d + 1)
-        a, b = sdist.slice_bounds(clo, chi, rank, world)
-        parts.append(bls.g1_to_raw(S.fold_msm(srs, (alpha, lo, scal), a, b)))
+    windows = [(max(lo, -d), min(lo + len(scal), d + 1)) for _, lo, scal in msms]
+    mine = sdist.deal_terms([chi - clo for clo, chi in windows], world)[rank]
+    for (alpha, lo, scal), (clo, chi), (a, b) in zip(msms, windows, mine):
+        parts.append(bls.g1_to_raw(S.fold_msm(srs, (alpha, lo, scal), clo + a, clo + b)))
     blob = b"".join(parts) + b"".join(bls.fr_to_bytes(v) for v in fvals)
     blobs = sdist.all_gather_bytes(blob)
     assert len(blobs) == world and blobs[rank] == blob
@@ -95,7 +95,7 @@ def test_plan_matches_prove_dense():
     assert S.assemble_proof_bytes(2, g48, fvals) == S.encode_proof(want)
 
 
-def test_job_dealing_is_balanced_and_total():
+def test_term_dealing_is_balanced_and_total():
     sys.path.insert(0, ROOT)
     from sonic_b200 import dist as sdist
 
@@ -103,11 +103,19 @@ def test_job_dealing_is_balanced_and_total():
     r, t, s_, c = 3 * n + 5, 7 * n + 9, 3 * n + 1, 2 * n + Q + 1
     lengths = [r, t, r - 1, r - 1, t - 1] + [s_, s_ - 1] * Q + [s_ - 1, c - 1] * Q + [c - 1, c]
     assert len(lengths) == 4 * Q + 7
-    for world in (2, 4, 8):
-        owner, by_job = sdist.deal_jobs(lengths, world)
-        assert by_job and sorted(set(owner)) == list(range(world))
-        load = [sum(l for l, o in zip(lengths, owner) if o == k) for k in range(world)]
-        assert max(load) * world <= sum(lengths) * 1.2
-    # a single huge MSM cannot be dealt: fall back to slicing
-    assert sdist.deal_jobs([1000, 10, 10], 2)[1] is False
-    assert sdist.deal_jobs([5], 2)[1] is False
+    for lens in (lengths, [1000, 10, 10], [5], [0, 3, 0, 0, 4], [1] * 7):
+        for world in (2, 3, 4, 8):
+            deal = sdist.deal_terms(lens, world)
+            load = [sum(b - a for a, b in parts) for parts in deal]
+            assert sum(load) == sum(lens) and max(load) - min(load) <= 1
+            split = 0
+            for m, L in enumerate(lens):
+                cuts = [deal[k][m] for k in range(world) if deal[k][m][1] > deal[k][m][0]]
+                # the parts of one MSM tile its window exactly, in rank order
+                assert sum(b - a for a, b in cuts) == L
+                assert all(cuts[i][1] == cuts[i + 1][0] for i in range(len(cuts) - 1))
+                assert not cuts or (cuts[0][0] == 0 and cuts[-1][1] == L)
+                split += len(cuts) > 1
+            assert split <= world - 1
+            # a rank's run is contiguous: at most two of its MSMs are partial
+            assert all(sum(1 for (a, b), L in zip(parts, lens) if 0 < b - a < L) <= 2 for parts in deal)
