@@ -180,13 +180,16 @@ k_msm_tile_prefix(uint32_t* __restrict__ hist_g, MsmTileTable tt, uint32_t per_j
     uint32_t* h = hist_g + (size_t)t0 * per_job + within;
     uint32_t run = 0;
     uint32_t t = t0;
-    for (; t + 4 <= t1; t += 4, h += 4 * (size_t)per_job) {
-        const uint32_t v0 = h[0], v1 = h[per_job], v2 = h[2 * (size_t)per_job], v3 = h[3 * (size_t)per_job];
-        h[0] = run;
-        h[per_job] = run + v0;
-        h[2 * (size_t)per_job] = run + v0 + v1;
-        h[3 * (size_t)per_job] = run + v0 + v1 + v2;
-        run += v0 + v1 + v2 + v3;
+    // eight independent loads in flight per thread before the (in-place) stores
+    for (; t + 8 <= t1; t += 8, h += 8 * (size_t)per_job) {
+        uint32_t v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = h[i * (size_t)per_job];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            h[i * (size_t)per_job] = run;
+            run += v[i];
+        }
     }
     for (; t < t1; ++t, h += per_job) {
         const uint32_t v = *h;
