@@ -587,6 +587,63 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
     }
     fr_from_mont(cx, suy.mont, suy.canon, suy.len);
 
+    // ---- which MSMs does this rank sum? -------------------------------------------------------------
+    // The shapes of the proof's MSMs (exponent of scalar 0 and length, record order) depend only on
+    // n, Q, M and d, so the dealing is known before any polynomial exists, and a rank of a sharded
+    // proof can skip what feeds only other ranks' MSMs: t(X,y) (two forward and one inverse NTT)
+    // unless it owns part of prT / prWt, and the quotient pass of openings it owns no part of.
+    // Every rank still evaluates everything that goes into the proof as a field value.
+    // Sharding: the (clipped) exponent windows of all MSMs, concatenated in
+    // record order, are cut into `world` equal runs of terms.  A rank so owns a few whole MSMs plus
+    // at most two partial ones -- sorting, bucket reduction and the tail shrink with the rank count,
+    // the loads differ by at most one term, and at most world-1 MSMs are split (their partial sums
+    // meet in the fold).  A deterministic function of the sizes: all ranks agree.  Mirrored by
+    // sonic_b200/dist.py:deal_terms.
+    struct Shape { int64_t lo; uint32_t len; };
+    std::vector<Shape> shape;
+    {
+        const int64_t nn = (int64_t)n;
+        const uint32_t rlen = 3 * n + 5, tlen = 7 * n + 9, ulen = 2 * n + Q + 1;
+        const int64_t rlo = -2 * nn - 4, tlo = -4 * nn - 8;
+        if (has_main) {
+            shape.push_back({rlo + (d - nn), rlen});   // prR
+            shape.push_back({tlo, tlen});              // prT
+            shape.push_back({rlo, rlen - 1});          // prWa
+            shape.push_back({rlo, rlen - 1});          // prWb
+            shape.push_back({tlo, tlen - 1});          // prWt
+        }
+        for (uint32_t j = 0; j < M; ++j) { shape.push_back({-nn, slen}); shape.push_back({-nn, slen - 1}); }      // S_j, W_j
+        for (uint32_t j = 0; j < M; ++j) { shape.push_back({-nn, slen - 1}); shape.push_back({-nn, ulen - 1}); }  // W'_j, Q_j
+        shape.push_back({-nn, ulen - 1});              // Q_v
+        shape.push_back({-nn, ulen});                  // C
+    }
+    const uint32_t nshape = (uint32_t)shape.size();
+    std::vector<int64_t> piece_lo(nshape), piece_hi(nshape);  // this rank's part [lo, hi) of every window, as exponents
+    {
+        uint64_t total_len = 0;
+        for (const Shape& sh : shape) {
+            const int64_t lo = sh.lo, hi = sh.lo + (int64_t)sh.len;
+            const int64_t clo = std::max(lo, -d), chi = std::max(clo, std::min(hi, d + 1));
+            total_len += (uint64_t)(chi - clo);
+        }
+        const uint64_t run_lo = sharded ? total_len * rank / world : 0;
+        const uint64_t run_hi = sharded ? total_len * (rank + 1) / world : total_len;
+        uint64_t run_pos = 0;
+        for (uint32_t i = 0; i < nshape; ++i) {
+            const int64_t lo = shape[i].lo, hi = shape[i].lo + (int64_t)shape[i].len;
+            const int64_t clo = std::max(lo, -d), chi = std::max(clo, std::min(hi, d + 1));
+            const uint64_t span = (uint64_t)(chi - clo);
+            const uint64_t a = run_lo > run_pos ? std::min(run_lo - run_pos, span) : 0;
+            const uint64_t b = run_hi > run_pos ? std::min(run_hi - run_pos, span) : 0;
+            run_pos += span;
+            piece_lo[i] = clo + (int64_t)a;
+            piece_hi[i] = clo + (int64_t)b;
+        }
+    }
+    auto owns = [&](uint32_t i) { return piece_hi[i] > piece_lo[i]; };
+    const uint32_t mbase = has_main ? 5u : 0u;  // record index of S_1
+    const bool need_t = has_main && (owns(1) || owns(4));
+
     // ---- r'(X,1), t(X,y) ------------------------------------------------------------------------
     Window rx1, txy;
     if (has_main) {
@@ -606,16 +663,20 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
         rx1.canon = ar.get<Fr>(rx1.len);
         SONIC_CUDA(cudaMemcpyAsync(rx1.mont, A, rx1.len * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
         fr_from_mont(cx, rx1.mont, rx1.canon, rx1.len);
-        SONIC_LAUNCH(k_build_rs, div_up(4 * n + 5, 256), 256, 0, rx1.mont, sxy_m, fwd(PT_Y), inv(PT_Y), n, B);
-        NttPlan plan = ntt_prepare(cx, logL);
-        ntt_forward(plan, A);
-        ntt_forward(plan, B);
-        fr_mul_pointwise(cx, A, B, (uint32_t)L);
-        ntt_inverse(plan, A);
-        SONIC_LAUNCH(k_t_fix, 1, 32, 0, A, circ->cs(), fwd(PT_Y), n, Q);
-        txy.mont = A;
-        txy.canon = ar.get<Fr>(txy.len);
-        fr_from_mont(cx, txy.mont, txy.canon, txy.len);
+        txy.mont = nullptr;
+        txy.canon = nullptr;
+        if (need_t) {
+            SONIC_LAUNCH(k_build_rs, div_up(4 * n + 5, 256), 256, 0, rx1.mont, sxy_m, fwd(PT_Y), inv(PT_Y), n, B);
+            NttPlan plan = ntt_prepare(cx, logL);
+            ntt_forward(plan, A);
+            ntt_forward(plan, B);
+            fr_mul_pointwise(cx, A, B, (uint32_t)L);
+            ntt_inverse(plan, A);
+            SONIC_LAUNCH(k_t_fix, 1, 32, 0, A, circ->cs(), fwd(PT_Y), n, Q);
+            txy.mont = A;
+            txy.canon = ar.get<Fr>(txy.len);
+            fr_from_mont(cx, txy.mont, txy.canon, txy.len);
+        }
     }
 
     // ---- openings: values and quotient vectors --------------------------------------------------
@@ -644,17 +705,18 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
     Quot q_a{}, q_b{}, q_t{}, q_v{};
     std::vector<Quot> q_wj(M), q_wpj(M), q_qj(M);
     if (has_main) {
-        q_a = add_open(rx1, ztabs, ztabs + tlz, true, &v_a);                 // Protocol.hs:79
-        q_b = add_open(rx1, fwd(PT_YZ), inv(PT_YZ), true, &v_b);            // Protocol.hs:80
-        q_t = add_open(txy, ztabs, ztabs + tlz, true, &v_t);                 // Protocol.hs:81
+        q_a = add_open(rx1, ztabs, ztabs + tlz, owns(2), &v_a);              // Protocol.hs:79
+        q_b = add_open(rx1, fwd(PT_YZ), inv(PT_YZ), owns(3), &v_b);         // Protocol.hs:80
+        if (need_t) q_t = add_open(txy, ztabs, ztabs + tlz, owns(4), &v_t);  // Protocol.hs:81 (t(z,y) itself is not a proof field)
+        else q_t = Quot{nullptr, txy.lo, txy.len - 1};
         add_open(sxy(0), ztabs, ztabs + tlz, false, &v_s);                   // Protocol.hs:83
     }
     for (uint32_t j = 0; j < M; ++j) {
-        q_wj[j] = add_open(sxy(1 + j), fwd(PT_ZJ + j), inv(PT_ZJ + j), true, &v_sj[j]);    // Signature.hs:43
-        q_wpj[j] = add_open(sxy(1 + j), fwd(PT_U), inv(PT_U), true, &v_wpj[j]);            // Signature.hs:54
-        q_qj[j] = add_open(suy, fwd(PT_YJ + j), inv(PT_YJ + j), true, &v_spj[j]);          // Signature.hs:55
+        q_wj[j] = add_open(sxy(1 + j), fwd(PT_ZJ + j), inv(PT_ZJ + j), owns(mbase + 2 * j + 1), &v_sj[j]);            // Signature.hs:43
+        q_wpj[j] = add_open(sxy(1 + j), fwd(PT_U), inv(PT_U), owns(mbase + 2 * M + 2 * j), &v_wpj[j]);                // Signature.hs:54
+        q_qj[j] = add_open(suy, fwd(PT_YJ + j), inv(PT_YJ + j), owns(mbase + 2 * M + 2 * j + 1), &v_spj[j]);          // Signature.hs:55
     }
-    q_v = add_open(suy, fwd(PT_V), inv(PT_V), true, &v_qv);                                 // Signature.hs:63
+    q_v = add_open(suy, fwd(PT_V), inv(PT_V), owns(mbase + 4 * M), &v_qv);                  // Signature.hs:63
     open_batch(cx, ojobs);
     SONIC_CUDA(cudaEventRecord(cx.ev[5], st));
 
@@ -680,24 +742,10 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
     SONIC_CUDA(cudaMemsetAsync(viol, 0xff, 12 * (size_t)nm, st));
     std::vector<MsmJob> jobs(nm);
     std::vector<int64_t> slice_lo(nm, 0);
-    // Sharding over `world` ranks: the (clipped) exponent windows of all MSMs,
-    // concatenated in record order, are cut into `world` equal runs of terms.  A rank so owns a few
-    // whole MSMs plus at most two partial ones -- sorting, bucket reduction and the tail shrink with
-    // the rank count, the loads differ by at most one term, and at most world-1 MSMs are split (their
-    // partial sums meet in the fold).  A deterministic function of the sizes: all ranks agree.
-    // Mirrored by sonic_b200/dist.py:deal_terms.
-    uint64_t run_lo = 0, run_hi = 0;
-    if (sharded) {
-        uint64_t total_len = 0;
-        for (uint32_t i = 0; i < nm; ++i) {
-            const int64_t lo = pm[i].lo, hi = pm[i].lo + (int64_t)pm[i].len;
-            const int64_t clo = std::max(lo, -d), chi = std::max(clo, std::min(hi, d + 1));
-            total_len += (uint64_t)(chi - clo);
-        }
-        run_lo = total_len * rank / world;
-        run_hi = total_len * (rank + 1) / world;
-    }
-    uint64_t run_pos = 0;
+    // the dealing was fixed from the shapes alone (above); the MSM list must agree with them
+    if (nm != nshape) return fail(SONIC_ERR_INVALID_ARG, "internal: MSM list does not match its shape table");
+    for (uint32_t i = 0; i < nm; ++i)
+        if (pm[i].lo != shape[i].lo || pm[i].len != shape[i].len) return fail(SONIC_ERR_INVALID_ARG, "internal: MSM %u does not match its shape", i);
     struct Rng { int64_t a, b; };
     std::vector<Rng> rngs(3 * (size_t)nm, Rng{0, 0});
     for (uint32_t i = 0; i < nm; ++i) {
@@ -708,20 +756,13 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
         if (m.family == SONIC_FAMILY_ALPHA && lo <= 0 && 0 < hi) r[1] = {0, 1};
         if (hi > d + 1) r[2] = {std::max(lo, d + 1), hi};
         for (int k = 0; k < 3; ++k) {
-            if (r[k].b > r[k].a) {
+            if (r[k].b > r[k].a && m.scal) {
                 const uint32_t a = (uint32_t)(r[k].a - lo), b = (uint32_t)(r[k].b - lo);
                 SONIC_LAUNCH(k_first_nonzero_job, div_up(b - a, 256), 256, 0, m.scal, a, b, viol + 3 * (size_t)i + k);
             }
         }
-        int64_t clo = std::max(lo, -d), chi = std::max(clo, std::min(hi, d + 1));
-        if (sharded) {  // the part of this window inside the rank's run of terms (often all or nothing)
-            const uint64_t span = (uint64_t)(chi - clo);
-            const uint64_t a = run_lo > run_pos ? std::min(run_lo - run_pos, span) : 0;
-            const uint64_t b = run_hi > run_pos ? std::min(run_hi - run_pos, span) : 0;
-            run_pos += span;
-            chi = clo + (int64_t)b;
-            clo = clo + (int64_t)a;
-        }
+        // the part of this window inside the rank's run of terms (the whole clipped window when not sharded)
+        const int64_t clo = piece_lo[i], chi = piece_hi[i];
         slice_lo[i] = clo;
         jobs[i].point_base = (uint32_t)srs->index(m.family, clo);
         jobs[i].n = (uint32_t)(chi - clo);
@@ -730,10 +771,14 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
         jobs[i].pad = 0;
     }
     // all scalar vectors live in the arena; express them as offsets from the lowest address
-    const Fr* sbase = pm[0].scal;
-    for (const ProofMsm& m : pm) if (m.scal < sbase) sbase = m.scal;
+    const Fr* sbase = nullptr;
+    for (uint32_t i = 0; i < nm; ++i) {
+        if (jobs[i].n == 0) continue;
+        if (!pm[i].scal) return fail(SONIC_ERR_INVALID_ARG, "internal: MSM %u has terms on this rank but no scalars", i);
+        if (!sbase || pm[i].scal < sbase) sbase = pm[i].scal;
+    }
     for (uint32_t i = 0; i < nm; ++i)
-        jobs[i].scalar_off = (uint32_t)((pm[i].scal - sbase) + (slice_lo[i] - pm[i].lo));
+        if (jobs[i].n) jobs[i].scalar_off = (uint32_t)((pm[i].scal - sbase) + (slice_lo[i] - pm[i].lo));
     G1Affine* d_aff = ar.get<G1Affine>(nm);
     uint8_t* d_comp = ar.get<uint8_t>((size_t)nm * 48);
     if (sharded) {

@@ -383,6 +383,10 @@ def test_prove_with_more_than_64_msms(gpu):
     assert gpu.prove_combine(Q, blobs) == got
     blobs = [gpu.prove_shard(g, ga, gc, rnd, r, 3) for r in range(3)]
     assert gpu.prove_combine(Q, blobs) == got
+    # more ranks than some MSMs have terms, and a rank count that does not divide anything
+    for world in (5, 8):
+        blobs = [gpu.prove_shard(g, ga, gc, rnd, r, world) for r in range(world)]
+        assert gpu.prove_combine(Q, blobs) == got, world
 
 
 def test_srs_g2_vectors(gpu):
