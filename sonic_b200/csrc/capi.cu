@@ -355,7 +355,9 @@ int sonic_srs_new(uint64_t d, const uint8_t x[32], const uint8_t alpha[32], soni
         if (pre_c < 0) {
             int lg = 0;
             while ((2ull << lg) <= d) ++lg;          // floor(log2 d)
-            pre_c = lg - 2;
+            // measured on prove() with d = 7n: n = 2^12 c = 13 (5.86 ms; 12: 5.94, 14: 6.11), n = 2^14 c = 15
+            // (15.1 ms; 14: 16.1, 16: 15.7), n = 2^16 c = 16 (49.5 ms; 15: 51.2, 17: 51.2)
+            pre_c = lg - 1;
             if (pre_c < 4) pre_c = 4;
             if (pre_c > 16) pre_c = 16;
             const uint64_t W = (255 + pre_c - 1) / pre_c;

@@ -355,10 +355,9 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const u
     const bool tiled = cx.opt_sort_mode != 0 && n_tot > 0 && sort_smem <= (size_t(128) << 10) && hist_len <= (1ull << 26);  // <= 256 MB of histograms
     cx.timing_ms["msm.sort_tiles"] = tiled ? tiles : 0;
     if (tiled) {
-        if (!cx.sort_smem_set) {
+        if (sort_smem > (size_t(48) << 10)) {  // opt-in above 48 KB; a host-side attribute, set per launch so that it follows the device
             SONIC_CUDA(cudaFuncSetAttribute(k_msm_sort_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10));
             SONIC_CUDA(cudaFuncSetAttribute(k_msm_sort_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10));
-            cx.sort_smem_set = true;
         }
         uint32_t* hist = ar.get<uint32_t>(hist_len);
         const dim3 grid(tiles, (unsigned)p.sets);
