@@ -87,6 +87,26 @@ def _prove_bytes(gpu, srs, c, rnd_ints):
     return out.raw
 
 
+def _prove_sharded_bytes(gpu, srs, c, rnd_ints, world):
+    """The same proof from `world` shard calls (run one after the other on this GPU) and the fold."""
+    from sonic_b200 import capi
+    L = capi.lib()
+    ch = ctypes.c_void_p()
+    capi.check(L.sonic_circuit_load(c["n"], c["Q"], c["wL"].ctypes.data, c["wR"].ctypes.data, c["wO"].ctypes.data,
+                                    c["cs"].ctypes.data, ctypes.byref(ch)))
+    rnd = np.frombuffer(synth.ints_to_bytes(rnd_ints), dtype=np.uint8).copy()
+    size = int(L.sonic_shard_blob_size(c["Q"]))
+    w = ctypes.c_uint64(0)
+    blobs = []
+    for rank in range(world):
+        blob = ctypes.create_string_buffer(size)
+        capi.check(L.sonic_prove_shard(srs._h, ch, c["aL"].ctypes.data, c["aR"].ctypes.data, c["aO"].ctypes.data, rnd.ctypes.data,
+                                       rank, world, blob, size, ctypes.byref(w)))
+        blobs.append(blob.raw[:w.value])
+    L.sonic_circuit_free(ch)
+    return gpu.prove_combine(c["Q"], blobs)
+
+
 def test_config2_prove_n4096_matches_reference_algorithm(gpu):
     """BASELINE config 2: synthetic circuit n = 2^12, Q = 8, d = 7n (3n+9 makes the reference's
     prove panic); the CUDA proof equals the C restatement's byte for byte, and the
@@ -102,6 +122,9 @@ def test_config2_prove_n4096_matches_reference_algorithm(gpu):
     want = cref.prove(table, d, n, Q, c["wL"], c["wR"], c["wO"], c["cs"], c["aL"], c["aR"], c["aO"],
                       np.frombuffer(synth.ints_to_bytes(rnd), dtype=np.uint8).copy(), threads=16)
     assert got == want
+    # sharded over 2, 4, 7 and 8 ranks (equal runs of MSM terms, Fr side by ownership): same bytes
+    for world in (2, 4, 7, 8):
+        assert _prove_sharded_bytes(gpu, srs, c, rnd, world) == got, world
     # commitR at d = 3n+9: r'(X,1) shifted by d - n stays inside the SRS
     d2 = 3 * n + 9
     srs2 = gpu.SRS.new(d2, x, alpha)
