@@ -620,24 +620,54 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
     const uint32_t nshape = (uint32_t)shape.size();
     std::vector<int64_t> piece_lo(nshape), piece_hi(nshape);  // this rank's part [lo, hi) of every window, as exponents
     {
-        uint64_t total_len = 0;
-        for (const Shape& sh : shape) {
-            const int64_t lo = sh.lo, hi = sh.lo + (int64_t)sh.len;
-            const int64_t clo = std::max(lo, -d), chi = std::max(clo, std::min(hi, d + 1));
-            total_len += (uint64_t)(chi - clo);
-        }
-        const uint64_t run_lo = sharded ? total_len * rank / world : 0;
-        const uint64_t run_hi = sharded ? total_len * (rank + 1) / world : total_len;
-        uint64_t run_pos = 0;
+        // clipped windows and their positions in the concatenation
+        std::vector<int64_t> clo(nshape);
+        std::vector<uint64_t> pos(nshape + 1, 0);
         for (uint32_t i = 0; i < nshape; ++i) {
             const int64_t lo = shape[i].lo, hi = shape[i].lo + (int64_t)shape[i].len;
-            const int64_t clo = std::max(lo, -d), chi = std::max(clo, std::min(hi, d + 1));
-            const uint64_t span = (uint64_t)(chi - clo);
-            const uint64_t a = run_lo > run_pos ? std::min(run_lo - run_pos, span) : 0;
-            const uint64_t b = run_hi > run_pos ? std::min(run_hi - run_pos, span) : 0;
-            run_pos += span;
-            piece_lo[i] = clo + (int64_t)a;
-            piece_hi[i] = clo + (int64_t)b;
+            clo[i] = std::max(lo, -d);
+            const int64_t chi = std::max(clo[i], std::min(hi, d + 1));
+            pos[i + 1] = pos[i] + (uint64_t)(chi - clo[i]);
+        }
+        const uint64_t total_len = pos[nshape];
+        const uint32_t W_ = sharded ? world : 1;
+        // run boundaries: equal runs first
+        std::vector<uint64_t> bound(W_ + 1);
+        for (uint32_t r = 0; r <= W_; ++r) bound[r] = total_len * r / W_;
+        // A rank that owns part of prT / prWt also builds t(X,y) (three NTTs), worth about 9n/8 terms
+        // of MSM work at n = 2^16: those ranks are dealt that much less, if the shorter runs leave the
+        // same ranks in charge of t (otherwise the equal runs stay).
+        auto t_owners = [&](const std::vector<uint64_t>& bd) {
+            std::vector<char> o(W_, 0);
+            for (uint32_t r = 0; r < W_; ++r)
+                for (uint32_t i : {1u, 4u}) {
+                    const uint64_t a = std::max(bd[r], pos[i]), b = std::min(bd[r + 1], pos[i + 1]);
+                    if (b > a) o[r] = 1;
+                }
+            return o;
+        };
+        if (sharded && has_main) {
+            const uint64_t V = (uint64_t)n + n / 8;
+            const std::vector<char> o1 = t_owners(bound);
+            uint64_t k = 0;
+            for (char c : o1) k += c;
+            const uint64_t padded = total_len + k * V;
+            std::vector<uint64_t> b2(W_ + 1, 0);
+            bool ok = k > 0 && k < W_;
+            for (uint32_t r = 0; r < W_ && ok; ++r) {
+                const uint64_t cap = padded * (r + 1) / W_ - padded * r / W_;
+                if (o1[r] && cap < V) { ok = false; break; }
+                b2[r + 1] = b2[r] + cap - (o1[r] ? V : 0);
+            }
+            if (ok && b2[W_] == total_len && t_owners(b2) == o1) bound = b2;
+        }
+        const uint64_t run_lo = sharded ? bound[rank] : 0, run_hi = sharded ? bound[rank + 1] : total_len;
+        for (uint32_t i = 0; i < nshape; ++i) {
+            const uint64_t span = pos[i + 1] - pos[i];
+            const uint64_t a = run_lo > pos[i] ? std::min(run_lo - pos[i], span) : 0;
+            const uint64_t b = run_hi > pos[i] ? std::min(run_hi - pos[i], span) : 0;
+            piece_lo[i] = clo[i] + (int64_t)a;
+            piece_hi[i] = clo[i] + (int64_t)b;
         }
     }
     auto owns = [&](uint32_t i) { return piece_hi[i] > piece_lo[i]; };

@@ -22,22 +22,42 @@ def slice_bounds(lo: int, hi: int, rank: int, world: int) -> Tuple[int, int]:
     return lo + span * rank // world, lo + span * (rank + 1) // world
 
 
-def deal_terms(lengths: Sequence[int], world: int) -> List[List[Tuple[int, int]]]:
+def deal_terms(lengths: Sequence[int], world: int, t_msms: Sequence[int] = (), t_extra: int = 0) -> List[List[Tuple[int, int]]]:
     """How prove_run (csrc/prove.cu) shards one proof: the (clipped) exponent windows of all MSMs,
-    concatenated in record order, are cut into `world` equal runs of terms.  Returns, per rank, the
+    concatenated in record order, are cut into `world` runs of terms.  Returns, per rank, the
     part [a, b) of every MSM's window (offsets into the window; a == b where the rank holds nothing).
-    A rank owns a few whole MSMs and at most two partial ones; at most world-1 MSMs are split."""
+    A rank owns a few whole MSMs and at most two partial ones; at most world-1 MSMs are split.
+    The runs are equal, except that ranks owning part of the MSMs `t_msms` (prT and prWt, records 1
+    and 4 of `prove`: those ranks also build t(X,y)) are dealt `t_extra` (= n + n/8) terms less when
+    that leaves the same ranks in charge of them."""
     total = sum(lengths)
+    pos = [0]
+    for n in lengths:
+        pos.append(pos[-1] + n)
+
+    def owners(bd):
+        return [any(min(bd[r + 1], pos[i + 1]) > max(bd[r], pos[i]) for i in t_msms) for r in range(world)]
+
+    bound = [total * r // world for r in range(world + 1)]
+    if t_msms and t_extra > 0:
+        o1 = owners(bound)
+        k = sum(o1)
+        padded = total + k * t_extra
+        b2, ok = [0], 0 < k < world
+        for r in range(world):
+            if not ok:
+                break
+            cap = padded * (r + 1) // world - padded * r // world
+            if o1[r] and cap < t_extra:
+                ok = False
+                break
+            b2.append(b2[-1] + cap - (t_extra if o1[r] else 0))
+        if ok and b2[-1] == total and owners(b2) == o1:
+            bound = b2
     out = []
     for rank in range(world):
-        lo, hi = total * rank // world, total * (rank + 1) // world
-        pos, parts = 0, []
-        for n in lengths:
-            a = min(max(lo - pos, 0), n)
-            b = min(max(hi - pos, 0), n)
-            parts.append((a, b))
-            pos += n
-        out.append(parts)
+        lo, hi = bound[rank], bound[rank + 1]
+        out.append([(min(max(lo - p, 0), n), min(max(hi - p, 0), n)) for p, n in zip(pos, lengths)])
     return out
 
 

@@ -43,7 +43,7 @@ def _worker(rank, world, port, result_dir):
     # this rank's shard blob: raw partial sums over its slice of every MSM, then the Fr values
     parts = []
     windows = [(max(lo, -d), min(lo + len(scal), d + 1)) for _, lo, scal in msms]
-    mine = sdist.deal_terms([chi - clo for clo, chi in windows], world)[rank]
+    mine = sdist.deal_terms([chi - clo for clo, chi in windows], world, t_msms=(1, 4), t_extra=12 + 12 // 8)[rank]
     for (alpha, lo, scal), (clo, chi), (a, b) in zip(msms, windows, mine):
         parts.append(bls.g1_to_raw(S.fold_msm(srs, (alpha, lo, scal), clo + a, clo + b)))
     blob = b"".join(parts) + b"".join(bls.fr_to_bytes(v) for v in fvals)
@@ -108,6 +108,18 @@ def test_term_dealing_is_balanced_and_total():
             deal = sdist.deal_terms(lens, world)
             load = [sum(b - a for a, b in parts) for parts in deal]
             assert sum(load) == sum(lens) and max(load) - min(load) <= 1
+            if len(lens) > 4:
+                # ranks that also build t(X,y) (owners of records 1 and 4) are dealt t_extra terms less
+                extra = n + n // 8 if lens is lengths else 1
+                deal = sdist.deal_terms(lens, world, t_msms=(1, 4), t_extra=extra)
+                load2 = [sum(b - a for a, b in parts) for parts in deal]
+                own = [any(parts[i][1] > parts[i][0] for i in (1, 4)) for parts in deal]
+                assert sum(load2) == sum(lens)
+                if load2 != load:
+                    heavy = [l for l, o in zip(load2, own) if o]
+                    light = [l for l, o in zip(load2, own) if not o]
+                    assert heavy and light and max(heavy) - min(heavy) <= 1 and max(light) - min(light) <= 1
+                    assert abs((min(light) - max(heavy)) - extra) <= 2
             split = 0
             for m, L in enumerate(lens):
                 cuts = [deal[k][m] for k in range(world) if deal[k][m][1] > deal[k][m][0]]
