@@ -140,11 +140,9 @@ void launch_accumulate_compact(Ctx& cx, uint32_t chunks, const uint32_t* entries
                                const G1Affine* points, G1XYZZ* buckets, G1XYZZ* head, G1XYZZ* tail) {
     (void)cx;
     const size_t smem = (size_t)ACC_SLOTS * 12 * 128 * sizeof(uint32_t);
-    static bool configured = false;
-    if (!configured) {
-        SONIC_CUDA(cudaFuncSetAttribute(k_msm_accumulate_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    // opt-in above 48 KB of dynamic shared memory: a host-side attribute of the current device's
+    // context, set per launch so that it survives sonic_shutdown / sonic_init on another device
+    SONIC_CUDA(cudaFuncSetAttribute(k_msm_accumulate_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SONIC_LAUNCH(k_msm_accumulate_compact, div_up(chunks, 128), 128, smem, entries, offsets, GB, L, points, buckets, head, tail);
 }
 
