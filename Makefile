@@ -8,7 +8,7 @@ HDRS := $(wildcard $(CSRC)/*.cuh) $(CSRC)/internal.h include/sonic_b200.h
 all: sonic_b200/libsonic_b200.so oracle
 
 sonic_b200/libsonic_b200.so: $(OBJS)
-	$(NVCC) -shared -o $@ $(OBJS) -lcudart
+	$(NVCC) -shared -o $@ $(OBJS) -lcudart -lnccl -ldl -lpthread
 
 $(CSRC)/build/g2srs.o: $(CSRC)/g2srs.cu $(HDRS)
 	@mkdir -p $(CSRC)/build

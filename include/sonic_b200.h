@@ -10,7 +10,9 @@
  *   G1  : 48 bytes, compressed: big-endian x; bit7 = 1, bit6 = infinity,
  *         bit5 = (y > (q-1)/2); infinity = 0xc0 || 0^47
  *   Ownership: the caller owns all buffers; the library copies in and never keeps a
- *   host pointer.  Handles are library-owned and immutable after creation.
+ *   host pointer.  Handles are library-owned; their contents never change after creation (an SRS
+ *   handle may additionally cache window tables derived from its points).
+ *   Threading: calls may come from any OS thread; the library runs one call at a time.
  *   Errors: 0 on success, a SONIC_ERR_* code otherwise; nothing is thrown across the
  *   boundary.  sonic_last_error() returns, for the calling thread, the text the
  *   reference would have passed to `panic` where there is one.
@@ -53,11 +55,22 @@ enum {
 typedef struct sonic_srs sonic_srs;
 typedef struct sonic_circuit sonic_circuit;
 
-/* Binds the calling process to one CUDA device (one process per GPU; multi-GPU runs
- * launch one process per device and exchange partial sums, see sonic_msm_g1_partial).
- * `devices`/`ndev`: ndev must be 1; devices[0] is the CUDA ordinal (NULL = device 0). */
+/* Binds the calling process to `ndev` CUDA devices of one box (1 <= ndev <= 8; `devices` = their CUDA
+ * ordinals, NULL = 0..ndev-1).  With ndev > 1 the library itself spreads the work:
+ * one context, stream and host worker thread per device, one NCCL communicator per device
+ * (ncclCommInitAll); every handle holds a replica per device.  The reference's entry points keep their
+ * signatures -- `prove` is still one call in one process (src/Sonic/Protocol.hs:47-53):
+ *   sonic_srs_new      each device generates 1/ndev of the exponent range (of every table level),
+ *                      one all-gather over NVLink                         (src/Sonic/SRS.hs:27-43)
+ *   sonic_prove        equal runs of the proof's MSM terms per device, one NCCL all-gather of the
+ *                      ~4 KB exchange records, `<>` per commitment on device 0
+ *   sonic_prove_batch  whole proofs dealt round-robin, no exchange
+ *   sonic_msm_g1, sonic_commit   contiguous slices of a long window, all-gather of 96-byte partial sums
+ * Everything else runs on devices[0].  (One process per GPU is still possible: sonic_prove_shard.) */
 int sonic_init(const int* devices, int ndev);
 void sonic_shutdown(void);
+/* number of devices this process is bound to (0 before sonic_init) */
+int sonic_device_count(void);
 
 const char* sonic_strerror(int code);
 /* copies the calling thread's last error text (NUL-terminated) into buf; returns its length */
@@ -71,8 +84,9 @@ void sonic_srs_free(sonic_srs* srs);
 uint64_t sonic_srs_d(const sonic_srs* srs); /* srsD, src/Sonic/SRS.hs:12 */
 
 /* SRS persistence (the reference has no on-disk format: SRS.hs:11-22 derives nothing):
- * the resident device arrays, precomputed levels included, as one file, so that a large setup is
- * paid once per machine rather than once per process.  The trapdoor is never stored. */
+ * the resident G1 arrays, full-range window tables included, as one file, so that a large setup is
+ * paid once per machine rather than once per process.  The trapdoor is never stored; neither are the
+ * optional G2 vectors nor tables restricted to a circuit size (those are rebuilt from the points). */
 int sonic_srs_save(const sonic_srs* srs, const char* path);
 int sonic_srs_load(const char* path, sonic_srs** out);
 
@@ -120,7 +134,7 @@ int sonic_msm_g1_device_partial(const sonic_srs* srs, int family, int64_t lo, ui
 
 /* ArithCircuit{weights = GateWeights{wL,wR,wO}, cs}  (src/Sonic/Protocol.hs:53; layout of
  * src/Sonic/Constraints.hs:38-53): three dense Q x n row-major matrices of Fr and Q constants,
- * kept resident across proofs. */
+ * kept resident across proofs.  Limits: n < 2^24, Q < 2^14, n Q < 2^28 (dense). */
 int sonic_circuit_load(uint64_t n, uint64_t Q, const uint8_t* wL, const uint8_t* wR,
                        const uint8_t* wO, const uint8_t* cs, sonic_circuit** out);
 /* Same circuit from sparse weights: each matrix in CSR -- rowptr (Q+1
@@ -148,15 +162,27 @@ int sonic_prove(const sonic_srs* srs, const sonic_circuit* circuit, const uint8_
                 const uint8_t* aR, const uint8_t* aO, const uint8_t* rnd, uint8_t* proof_out,
                 uint64_t cap, uint64_t* written);
 
-/* One proof sharded over `world` processes (one per GPU).  Every rank calls
- * sonic_prove_shard with the same inputs.  The exponent windows of the proof's 4Q+7 MSMs,
- * concatenated in record order, are cut into `world` runs of terms (equal, except that the ranks
- * that also build t(X,y) get 9n/8 terms less): a rank sums a few whole
- * MSMs plus at most two partial ones (the identity for the rest), computes every field value of
- * the proof, but only the polynomials its own MSMs need (t(X,y) only where part of prT / prWt
- * lives), and returns a shard blob of sonic_shard_blob_size(Q) bytes
- * (4Q+7 raw partial sums + the 2Q+5 field values).  The ranks exchange the blobs (one NCCL
- * all-gather); sonic_prove_combine folds them (`<>` per commitment) into the proof bytes. */
+/* `count` independent proofs of one circuit in one call (BASELINE config 5: 64 proofs at n = 2^14).
+ * assignments: count x (aL | aR | aO), 3n Fr each; rnds: count x sonic_rnd_count(Q) Fr; proofs_out:
+ * count x sonic_proof_size(Q) bytes.  Proof i is `prove` on (assignment i, draws i): with several
+ * devices, proof i runs on device i mod ndev, all devices at the same time, nothing exchanged. */
+int sonic_prove_batch(const sonic_srs* srs, const sonic_circuit* circuit, uint64_t count, const uint8_t* assignments,
+                      const uint8_t* rnds, uint8_t* proofs_out, uint64_t cap, uint64_t* written);
+
+/* One proof sharded over `world` PROCESSES (one per GPU; the multi-process twin of sonic_init with
+ * ndev > 1).  Every rank calls sonic_prove_shard with the same inputs.  The exponent windows of the
+ * proof's 4Q+7 MSMs, concatenated in record order, are cut into `world` runs of terms (equal, except
+ * that the ranks that also build t(X,y) get 9n/8 terms less): a rank sums a few whole MSMs plus at
+ * most two partial ones (the identity for the rest) and builds only the polynomials, power tables and
+ * openings those MSMs need; a field value of the proof is computed by the lowest rank that opens the
+ * polynomial it belongs to.  The result is an exchange record of sonic_shard_exchange_size(Q) bytes:
+ *   (4Q+7) raw partial sums (96 B) | (2Q+3) field values (zeros where another rank leads) |
+ *   status words: per MSM the first non-zero coefficient outside the SRS, the encoding flag, srsD
+ * and the shard blob = record | hscU | hscV.  The ranks exchange the records (one NCCL all-gather);
+ * sonic_prove_combine folds them: `<>` per commitment, the one contribution per field value, the
+ * minimum of the violation flags -- so every rank that folds reaches the same verdict, success or the
+ * reference's panic text, whichever rank saw the offending coefficient. */
+uint64_t sonic_shard_exchange_size(uint64_t Q);
 uint64_t sonic_shard_blob_size(uint64_t Q);
 int sonic_prove_shard(const sonic_srs* srs, const sonic_circuit* circuit, const uint8_t* aL,
                       const uint8_t* aR, const uint8_t* aO, const uint8_t* rnd, uint32_t rank,
@@ -164,16 +190,16 @@ int sonic_prove_shard(const sonic_srs* srs, const sonic_circuit* circuit, const 
 int sonic_prove_combine(uint64_t Q, uint32_t world, const uint8_t* blobs, uint8_t* proof_out,
                         uint64_t cap, uint64_t* written);
 
-/* Exchange on the device: sonic_prove_shard_sink additionally leaves the 4Q+7 raw partial sums
- * (96 B each) at `d_partials_out`, a device buffer of the caller -- typically the input of an NCCL
- * all-gather -- and sonic_prove_combine_device folds the gathered device buffer ([world][4Q+7] x 96 B)
- * directly; the field values are the same on every rank and come from the rank's own blob.
+/* Exchange on the device: sonic_prove_shard_sink leaves the exchange record at `d_record_out`, a device
+ * buffer of the caller (sonic_shard_exchange_size(Q) bytes) -- typically the input of an NCCL
+ * all-gather -- and sonic_prove_combine_device folds the gathered device buffer ([world] records)
+ * directly; `own_blob` only supplies hscU, hscV.  blob_out may be NULL when d_record_out is given.
  * `assignment`: aL | aR | aO contiguous (3n Fr), host or device as flagged; `d_rnd_or_null`: the
  * draws in device memory if already there. */
 int sonic_prove_shard_sink(const sonic_srs* srs, const sonic_circuit* circuit, const void* assignment,
                            int assignment_on_device, const void* d_rnd_or_null, const uint8_t* rnd_host,
                            uint32_t rank, uint32_t world, uint8_t* blob_out, uint64_t cap,
-                           uint64_t* written, void* d_partials_out);
+                           uint64_t* written, void* d_record_out);
 int sonic_prove_combine_device(uint64_t Q, uint32_t world, const void* d_gathered, const uint8_t* own_blob,
                                uint8_t* proof_out, uint64_t cap, uint64_t* written);
 
@@ -209,8 +235,11 @@ int sonic_pcv_fold(uint64_t k, const uint8_t* F48, const uint8_t* W48, const uin
 /* ---- tuning and measurement hooks (not part of the reference surface) ---- */
 /* option names: "window_bits" (0 = automatic), "chunk" (0 = automatic),
  * "precompute" (-1 = automatic, 0 = off, c = window bits): SRS.new also stores the multiples
- * 2^(c j) * base of every SRS element so that all windows of an MSM share one bucket set;
+ * 2^(c j) * base of every SRS element so that all windows of an MSM share one bucket set; when those
+ * full-range tables exceed the budget, the first proof of a circuit size builds tables for the 17n+23
+ * exponents that size reads (by doubling the resident points; kept in the SRS handle);
  * "precompute_budget_mb": HBM the automatic mode may spend on those tables (default 8192);
+ * "shard_min_terms": a standalone MSM is cut across the devices when it has at least this many terms per device (default 2^17);
  * "g2" (0/1): SRS.new also generates the G2 vectors; "sort_mode" (0: thread per term with global
  * atomics, 1: tiled counting sort with shared-memory histograms [default], 2..64: tiled with that
  * many tiles per SM), "acc_mode", "acc_blocks", "reduce_mode", "reduce_k": kernel tuning knobs
@@ -221,6 +250,8 @@ int sonic_set_option(const char* name, int64_t value);
  * the same call also reports counters of the last MSM batch: "msm.window_bits", "msm.windows",
  * "msm.terms", "msm.entries", "msm.jobs", "msm.chunk", "msm.buckets", "msm.sort_tiles" */
 double sonic_last_timing_ms(const char* stage);
+/* the same for device `slot` of the sonic_init list (each device times its own share of a call) */
+double sonic_last_timing_ms_dev(int slot, const char* stage);
 /* number of kernel launches issued by this library since sonic_init */
 uint64_t sonic_launch_count(void);
 /* CUDA events on the library's own stream, for harnesses that time several calls as one

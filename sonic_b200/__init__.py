@@ -6,7 +6,7 @@ The names follow sdiehl/sonic (`SRS.new`, `commitPoly`, `openPoly`, `prove`, `hs
 INTEGRATION.md would.  There is no CPU implementation behind these functions: importing
 works anywhere, but the first call raises if the CUDA library or a GPU is missing.
 """
-from .capi import SonicError, lib, init, shutdown, set_option, last_timing_ms, launch_count  # noqa: F401
+from .capi import SonicError, lib, init, shutdown, set_option, last_timing_ms, launch_count, device_count  # noqa: F401
 from .api import (  # noqa: F401
     ArithCircuit,
     Assignment,
@@ -23,6 +23,7 @@ from .api import (  # noqa: F401
     openPoly,
     pcv_fold,
     prove_shard,
+    prove_batch,
     prove_combine,
     prove,
     prove_bytes,

@@ -81,6 +81,16 @@ class _Circuit:
         if not w.wL or not w.wL[0]:
             raise SonicError(1, "Empty weights")
         self.Q, self.n = len(w.wL), len(w.wL[0])
+        # the C side copies Q*n (and Q) field elements from these buffers: every shape is checked here.
+        # (The reference indexes rows with `!!` and would fail on a ragged matrix too.)
+        for name, m in (("wL", w.wL), ("wR", w.wR), ("wO", w.wO)):
+            if len(m) != self.Q:
+                raise SonicError(1, f"{name} has {len(m)} rows, expected Q = {self.Q}")
+            for q, row in enumerate(m):
+                if len(row) != self.n:
+                    raise SonicError(1, f"{name}[{q}] has {len(row)} entries, expected n = {self.n}")
+        if len(c.cs) != self.Q:
+            raise SonicError(1, f"cs has {len(c.cs)} entries, expected Q = {self.Q}")
         h = c_void_p()
         if c.sparse:
             import numpy as np
@@ -317,14 +327,19 @@ def parse_proof(buf: bytes, Q: int) -> Proof:
                  prS=F(304), prHscProof=_parse_hsc(buf, Q, 336))
 
 
+def _check_prove_inputs(ch: "_Circuit", assignment: Assignment, rnd: Sequence[int]) -> None:
+    """The C ABI reads n Fr from each of aL/aR/aO and 2Q+8 Fr from rnd: lengths are checked before any pointer crosses."""
+    if not (len(assignment.aL) == len(assignment.aR) == len(assignment.aO) == ch.n):
+        raise SonicError(1, "assignment length differs from the circuit's n")
+    if len(rnd) != 2 * ch.Q + 8:
+        raise SonicError(1, "prove draws 2Q+8 random field elements")
+
+
 def prove_bytes(srs: SRS, assignment: Assignment, circuit: ArithCircuit, rnd: Sequence[int]) -> bytes:
     """The boundary call itself: one `sonic_prove`, proof bytes in record order."""
     ch = circuit.handle()
     n, Q = ch.n, ch.Q
-    if not (len(assignment.aL) == len(assignment.aR) == len(assignment.aO) == n):
-        raise SonicError(1, "assignment length differs from the circuit's n")
-    if len(rnd) != 2 * Q + 8:
-        raise SonicError(1, "prove draws 2Q+8 random field elements")
+    _check_prove_inputs(ch, assignment, rnd)
     size = int(lib().sonic_proof_size(Q))
     out = ctypes.create_string_buffer(size)
     written = c_uint64(0)
@@ -348,6 +363,8 @@ def hscProve(srs: SRS, circuit: ArithCircuit, yzs: Sequence[Tuple[int, int]], u:
     (`sPoly weights`), `u` and `v` are its two `rnd` draws."""
     ch = circuit.handle()
     m = len(yzs)
+    if any(len(p) != 2 for p in yzs):
+        raise SonicError(1, "yzs holds (y_j, z_j) pairs")
     size = (4 * m + 2) * 48 + (2 * m + 2) * 32
     out = ctypes.create_string_buffer(size)
     written = c_uint64(0)
@@ -359,6 +376,9 @@ def hscProve(srs: SRS, circuit: ArithCircuit, yzs: Sequence[Tuple[int, int]], u:
 def prove_shard(srs: SRS, assignment: Assignment, circuit: ArithCircuit, rnd: Sequence[int], rank: int, world: int) -> bytes:
     """This rank's share of one proof (sonic_prove_shard): raw partial sums + field values."""
     ch = circuit.handle()
+    _check_prove_inputs(ch, assignment, rnd)
+    if not (world >= 2 and 0 <= rank < world):
+        raise SonicError(1, "need world >= 2 and 0 <= rank < world")
     size = int(lib().sonic_shard_blob_size(ch.Q))
     out = ctypes.create_string_buffer(size)
     written = c_uint64(0)
@@ -367,9 +387,31 @@ def prove_shard(srs: SRS, assignment: Assignment, circuit: ArithCircuit, rnd: Se
     return out.raw[:written.value]
 
 
+def prove_batch(srs: SRS, assignments: Sequence[Assignment], circuit: ArithCircuit, rnds: Sequence[Sequence[int]]) -> List[bytes]:
+    """`mapM (prove srs ?? circuit)` over independent assignments in one call (sonic_prove_batch): with
+    several devices whole proofs are dealt round-robin and run at the same time."""
+    ch = circuit.handle()
+    if len(assignments) != len(rnds):
+        raise SonicError(1, "one list of draws per assignment")
+    for a, r in zip(assignments, rnds):
+        _check_prove_inputs(ch, a, r)
+    count = len(assignments)
+    size = int(lib().sonic_proof_size(ch.Q))
+    out = ctypes.create_string_buffer(size * max(count, 1))
+    written = c_uint64(0)
+    flat_a = b"".join(_frs(a.aL) + _frs(a.aR) + _frs(a.aO) for a in assignments)
+    flat_r = b"".join(_frs(r) for r in rnds)
+    check(lib().sonic_prove_batch(srs._h, ch.h, count, flat_a, flat_r, out, size * count, ctypes.byref(written)))
+    raw = out.raw
+    return [raw[i * size:(i + 1) * size] for i in range(count)]
+
+
 def prove_combine(Q: int, blobs: Sequence[bytes]) -> bytes:
     """Folds the gathered shard blobs into the proof bytes (sonic_prove_combine)."""
     capi.init()
+    want = int(lib().sonic_shard_blob_size(Q))
+    if not blobs or any(len(b) != want for b in blobs):
+        raise SonicError(1, f"every shard blob must be {want} bytes")
     size = int(lib().sonic_proof_size(Q))
     out = ctypes.create_string_buffer(size)
     written = c_uint64(0)

@@ -34,6 +34,7 @@ _u8p = c_void_p
 SYMBOLS = {
     "sonic_init": (c_int, [POINTER(c_int), c_int]),
     "sonic_shutdown": (None, []),
+    "sonic_device_count": (c_int, []),
     "sonic_strerror": (c_char_p, [c_int]),
     "sonic_last_error": (c_size_t, [ctypes.c_char_p, c_size_t]),
     "sonic_srs_new": (c_int, [c_uint64, _u8p, _u8p, POINTER(c_void_p)]),
@@ -57,6 +58,8 @@ SYMBOLS = {
     "sonic_rnd_count": (c_uint64, [c_uint64]),
     "sonic_proof_size": (c_uint64, [c_uint64]),
     "sonic_prove": (c_int, [c_void_p, c_void_p, _u8p, _u8p, _u8p, _u8p, _u8p, c_uint64, POINTER(c_uint64)]),
+    "sonic_prove_batch": (c_int, [c_void_p, c_void_p, c_uint64, _u8p, _u8p, _u8p, c_uint64, POINTER(c_uint64)]),
+    "sonic_shard_exchange_size": (c_uint64, [c_uint64]),
     "sonic_shard_blob_size": (c_uint64, [c_uint64]),
     "sonic_prove_shard": (c_int, [c_void_p, c_void_p, _u8p, _u8p, _u8p, _u8p, ctypes.c_uint32, ctypes.c_uint32, _u8p, c_uint64, POINTER(c_uint64)]),
     "sonic_prove_shard_sink": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, _u8p, ctypes.c_uint32, ctypes.c_uint32, _u8p, c_uint64, POINTER(c_uint64), c_void_p]),
@@ -68,6 +71,7 @@ SYMBOLS = {
     "sonic_pcv_fold": (c_int, [c_uint64, _u8p, _u8p, _u8p, _u8p, _u8p, c_void_p, ctypes.c_uint32, _u8p]),
     "sonic_set_option": (c_int, [c_char_p, c_int64]),
     "sonic_last_timing_ms": (c_double, [c_char_p]),
+    "sonic_last_timing_ms_dev": (c_double, [c_int, c_char_p]),
     "sonic_launch_count": (c_uint64, []),
     "sonic_bench_mark": (c_int, [c_int]),
     "sonic_bench_elapsed_ms": (c_double, [c_int, c_int]),
@@ -81,6 +85,24 @@ SYMBOLS = {
 }
 
 
+def _preload_nccl() -> None:
+    """libsonic_b200.so links libnccl.so.2 (the in-library multi-GPU exchange).  A Python process that
+    also imports torch must end up with ONE NCCL: torch's wheel bundles its own under the same soname,
+    and the loader keeps whichever came first.  Load the bundled one first when it is installed, so that
+    the order of `import torch` / `import sonic_b200` does not matter; a process without torch gets the
+    system library through the normal search path."""
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            path = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+    except Exception:
+        pass
+
+
 def lib():
     """Loads libsonic_b200.so; raises (loudly) when it has not been built."""
     global _lib
@@ -88,6 +110,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise SonicError(8, f"{LIB_PATH} is missing: build it with `make` / `__graft_entry__.build()`; "
                                 "there is no CPU fallback")
+        _preload_nccl()
         L = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)
@@ -108,16 +131,23 @@ def check(rc: int) -> None:
         raise SonicError(rc, last_error())
 
 
-def init(device: int | None = None) -> None:
-    """Binds this process to one GPU (LOCAL_RANK under torchrun, else device 0)."""
+def init(device=None) -> None:
+    """Binds this process to one GPU (an int; default LOCAL_RANK under torchrun, else device 0) or to
+    several GPUs of the box (a list of CUDA ordinals: the library then shards SRS.new, prove and
+    prove_batch over them itself, include/sonic_b200.h: sonic_init)."""
     global _ready
     if _ready:
         return
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0"))
-    dev = (c_int * 1)(device)
-    check(lib().sonic_init(dev, 1))
+    devices = list(device) if isinstance(device, (list, tuple)) else [int(device)]
+    dev = (c_int * len(devices))(*devices)
+    check(lib().sonic_init(dev, len(devices)))
     _ready = True
+
+
+def device_count() -> int:
+    return int(lib().sonic_device_count())
 
 
 def shutdown() -> None:
@@ -131,8 +161,8 @@ def set_option(name: str, value: int) -> None:
     check(lib().sonic_set_option(name.encode(), value))
 
 
-def last_timing_ms(stage: str = "total") -> float:
-    return float(lib().sonic_last_timing_ms(stage.encode()))
+def last_timing_ms(stage: str = "total", slot: int = 0) -> float:
+    return float(lib().sonic_last_timing_ms_dev(slot, stage.encode()))
 
 
 def launch_count() -> int:

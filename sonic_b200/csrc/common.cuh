@@ -103,9 +103,12 @@ struct Arena {
     }
 };
 
+constexpr int MAX_DEV = 8;  // the GPUs of one NVSwitch box
+
 struct Ctx {
     bool ready = false;
-    int device = 0;
+    int device = 0;                                       // CUDA ordinal
+    int slot = 0;                                         // position in the sonic_init device list (= rank of in-library sharding)
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     Arena arena;
@@ -130,9 +133,21 @@ struct Ctx {
     size_t pinned_cap = 0;
 };
 
-inline Ctx& ctx() {
-    static Ctx c;
+// One context per device of the sonic_init list.  Kernels are launched on "the current context's"
+// stream: the calling thread's by default slot 0; every per-device worker thread of a multi-GPU
+// runtime binds its own slot once (ctx_bind), so the launchers below need no device argument.
+inline Ctx* ctx_slots() {
+    static Ctx c[MAX_DEV];
     return c;
+}
+inline Ctx*& ctx_current() {
+    static thread_local Ctx* p = nullptr;
+    return p;
+}
+inline void ctx_bind(Ctx* c) { ctx_current() = c; }
+inline Ctx& ctx() {
+    Ctx* p = ctx_current();
+    return p ? *p : ctx_slots()[0];
 }
 
 #define SONIC_LAUNCH(kernel, grid, block, smem, ...)                          \

@@ -42,12 +42,14 @@ __global__ void k_fr_inv(const Fr* __restrict__ in, Fr* __restrict__ out, int n)
 // a run of 64 powers per thread: the 64-bit-exponent start (about 27 products at k ~ 2^18) is then a
 // third of the run instead of twice it; the tables are compute-bound (9 M entries per proof)
 constexpr int POW_RUN = 64;
-__global__ void __launch_bounds__(128) k_pow_tables(const Fr* __restrict__ bases, Fr* __restrict__ tab, uint64_t len, uint64_t stride) {
+__global__ void __launch_bounds__(128) k_pow_tables(const Fr* __restrict__ bases, Fr* __restrict__ tab, uint64_t len, uint64_t stride,
+                                                    const uint32_t* __restrict__ sel) {
     const uint64_t k0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * POW_RUN;
     if (k0 >= len) return;
-    const Fr b = bases[blockIdx.y];
+    const uint32_t row = sel ? sel[blockIdx.y] : blockIdx.y;
+    const Fr b = bases[row];
     Fr v = fp_pow_u64(b, k0);
-    Fr* o = tab + (size_t)blockIdx.y * stride + k0;
+    Fr* o = tab + (size_t)row * stride + k0;
     for (int i = 0; i < POW_RUN && k0 + i < len; ++i) {
         o[i] = v;
         v = fp_mul(v, b);
@@ -297,7 +299,7 @@ NttPlan ntt_prepare(Ctx& cx, uint32_t logL) {
     p.tw = mem + 4;
     p.twi = p.tw + half;
     SONIC_LAUNCH(k_ntt_params, 1, 32, 0, logL, p.params);
-    SONIC_LAUNCH(k_pow_tables, dim3(div_up(div_up(half, POW_RUN), 128), 2), 128, 0, p.params, p.tw, half, half);
+    SONIC_LAUNCH(k_pow_tables, dim3(div_up(div_up(half, POW_RUN), 128), 2), 128, 0, p.params, p.tw, half, half, (const uint32_t*)nullptr);
     return p;
 }
 
@@ -361,9 +363,9 @@ void fr_mul_pointwise(Ctx& cx, Fr* a, const Fr* b, uint32_t n) {
     if (n) SONIC_LAUNCH(k_fr_mul_pointwise, div_up(n, 256), 256, 0, a, b, n);
 }
 
-void pow_tables(Ctx& cx, const Fr* bases, int ntab, Fr* tab, uint64_t len, uint64_t stride) {
+void pow_tables(Ctx& cx, const Fr* bases, int ntab, Fr* tab, uint64_t len, uint64_t stride, const uint32_t* d_sel) {
     (void)cx;
-    if (ntab && len) SONIC_LAUNCH(k_pow_tables, dim3(div_up(div_up(len, POW_RUN), 128), (unsigned)ntab), 128, 0, bases, tab, len, stride);
+    if (ntab && len) SONIC_LAUNCH(k_pow_tables, dim3(div_up(div_up(len, POW_RUN), 128), (unsigned)ntab), 128, 0, bases, tab, len, stride, d_sel);
 }
 
 void open_batch(Ctx& cx, const std::vector<OpenJob>& jobs) {

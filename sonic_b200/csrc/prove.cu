@@ -17,6 +17,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "internal.h"
 
 namespace sonic {
@@ -41,7 +43,7 @@ __global__ void __launch_bounds__(256) k_build_r(const Fr* __restrict__ aL, cons
 __global__ void __launch_bounds__(128) k_build_sxy(const Fr* __restrict__ wL, const Fr* __restrict__ wR, const Fr* __restrict__ wO,
                                                    uint32_t n, uint32_t Q, const Fr* __restrict__ tabs, uint64_t tl,
                                                    const uint32_t* __restrict__ fwd_idx, const uint32_t* __restrict__ inv_idx,
-                                                   Fr* __restrict__ out) {
+                                                   const uint32_t* __restrict__ slot_idx, Fr* __restrict__ out) {
     const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
     if (i0 >= n) return;
     const uint32_t b = blockIdx.y;
@@ -57,7 +59,7 @@ __global__ void __launch_bounds__(128) k_build_sxy(const Fr* __restrict__ wL, co
         sw = fp_add(sw, fp_mul(yp, wO[w]));
     }
     sw = fp_sub(fp_sub(sw, yt[i]), yi[i]);
-    Fr* o = out + (size_t)b * (3 * (size_t)n + 1);
+    Fr* o = out + (size_t)slot_idx[b] * (3 * (size_t)n + 1);
     o[n - i] = su;        // u_i(y) X^-i
     o[n + i] = sv;        // v_i(y) X^i
     o[2 * n + i] = sw;    // w_i(y) X^(i+n)
@@ -149,7 +151,7 @@ struct SparseView {
 __global__ void __launch_bounds__(128) k_build_sxy_csc(SparseView L, SparseView R_, SparseView O, uint32_t n,
                                                        const Fr* __restrict__ tabs, uint64_t tl,
                                                        const uint32_t* __restrict__ fwd_idx, const uint32_t* __restrict__ inv_idx,
-                                                       Fr* __restrict__ out) {
+                                                       const uint32_t* __restrict__ slot_idx, Fr* __restrict__ out) {
     const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
     if (i0 >= n) return;
     const uint32_t b = blockIdx.y;
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(128) k_build_sxy_csc(SparseView L, SparseView 
     for (uint32_t k = R_.ptr[i0]; k < R_.ptr[i0 + 1]; ++k) sv = fp_add(sv, fp_mul(yt[n + 1 + R_.idx[k]], R_.val[k]));
     for (uint32_t k = O.ptr[i0]; k < O.ptr[i0 + 1]; ++k) sw = fp_add(sw, fp_mul(yt[n + 1 + O.idx[k]], O.val[k]));
     sw = fp_sub(fp_sub(sw, yt[i]), yi[i]);
-    Fr* o = out + (size_t)b * (3 * (size_t)n + 1);
+    Fr* o = out + (size_t)slot_idx[b] * (3 * (size_t)n + 1);
     o[n - i] = su;
     o[n + i] = sv;
     o[2 * n + i] = sw;
@@ -197,9 +199,9 @@ __global__ void __launch_bounds__(256) k_build_suy_dot_csr(SparseView L, SparseV
 
 // derived scalars: pts[] = the evaluation points (Montgomery), pts[np..2np) their inverses
 // rnd_m: 2M+8 draws (Montgomery), M = number of (y_j, z_j) pairs.  Layout of pts: y, z, yz, y_1..y_M, z_1..z_M, u, v
-__global__ void k_prove_points(const Fr* __restrict__ rnd_m, uint32_t M, int has_main, Fr* __restrict__ pts) {
+__global__ void k_prove_points(const Fr* __restrict__ rnd_m, uint32_t M, int has_main, const uint32_t* __restrict__ sel, Fr* __restrict__ pts) {
     const uint32_t np = 2 * M + 5;
-    const uint32_t t = blockIdx.x;   // one single-thread block per point: the Euclid inverse branches on the data
+    const uint32_t t = sel[blockIdx.x];   // one single-thread block per point: the Euclid inverse branches on the data
     if (t >= np || threadIdx.x != 0) return;
     Fr v;
     if (t == 0) v = has_main ? rnd_m[4] : Fr::one();
@@ -219,7 +221,8 @@ __global__ void __launch_bounds__(256) k_first_nonzero_job(const Fr* __restrict_
 
 }  // namespace sonic
 
-// resident circuit (weights in Montgomery form)
+namespace sonic {
+// resident circuit (weights in Montgomery form), one replica per device
 // One sparse weight matrix on the device, both ways: by row (CSR: the Y^(n+q) dot products of
 // s(u,Y) walk rows) and by column (CSC: every X-coefficient of s(X,y) sums one column).
 struct SparseMat {
@@ -232,7 +235,7 @@ struct SparseMat {
     uint64_t nnz = 0;
 };
 
-struct sonic_circuit {
+struct CircuitRep {
     uint64_t n = 0, Q = 0;
     bool sparse = false;
     sonic::Fr* w = nullptr;   // dense: wL | wR | wO, each Q*n row-major, then cs (Q); sparse: cs only
@@ -244,12 +247,10 @@ struct sonic_circuit {
     sonic::Fr* cs() const { return sparse ? w : w + 3 * Q * n; }
 };
 
-namespace sonic {
-
 int circuit_load(Ctx& cx, uint64_t n, uint64_t Q, const uint8_t* wL, const uint8_t* wR, const uint8_t* wO,
-                 const uint8_t* cs, sonic_circuit** out) {
+                 const uint8_t* cs, CircuitRep** out) {
     const uint64_t m = Q * n;
-    sonic_circuit* c = new sonic_circuit;
+    CircuitRep* c = new CircuitRep;
     c->n = n;
     c->Q = Q;
     cudaError_t e = cudaMalloc((void**)&c->w, (3 * m + Q) * sizeof(Fr));
@@ -284,7 +285,7 @@ int circuit_load(Ctx& cx, uint64_t n, uint64_t Q, const uint8_t* wL, const uint8
 // nnz x 32 canonical bytes).  The column-major copy is built here on the host (index shuffling
 // only; every field operation stays on the device).
 int circuit_load_csr(Ctx& cx, uint64_t n, uint64_t Q, const uint64_t* const row_ptr[3], const uint32_t* const col[3],
-                     const uint8_t* const val[3], const uint8_t* cs, sonic_circuit** out) {
+                     const uint8_t* const val[3], const uint8_t* cs, CircuitRep** out) {
     uint64_t nnz[3], total = 0;
     for (int m = 0; m < 3; ++m) {
         if (row_ptr[m][0] != 0) return fail(SONIC_ERR_INVALID_ARG, "CSR row_ptr must start at 0");
@@ -333,7 +334,7 @@ int circuit_load_csr(Ctx& cx, uint64_t n, uint64_t Q, const uint64_t* const row_
     memcpy(&vals[vw * 32], cs, Q * 32);
     vw += Q;
 
-    sonic_circuit* c = new sonic_circuit;
+    CircuitRep* c = new CircuitRep;
     c->n = n;
     c->Q = Q;
     c->sparse = true;
@@ -377,10 +378,7 @@ int circuit_load_csr(Ctx& cx, uint64_t n, uint64_t Q, const uint64_t* const row_
     return SONIC_OK;
 }
 
-uint64_t circuit_n(const sonic_circuit* c) { return c->n; }
-uint64_t circuit_Q(const sonic_circuit* c) { return c->Q; }
-
-void circuit_free(sonic_circuit* c) {
+void circuit_free(CircuitRep* c) {
     if (!c) return;
     if (c->sparse) { if (c->blob) cudaFree(c->blob); }
     else if (c->w) cudaFree(c->w);
@@ -399,7 +397,7 @@ struct Window {  // a dense vector and the exponent of its slot 0
 // One MSM of the proof, in the order the proof record lists its G1 fields.
 struct ProofMsm {
     int family;
-    const Fr* scal;   // canonical scalars, slot 0 <-> exponent lo
+    const Fr* scal;   // canonical scalars, slot 0 <-> exponent lo (null: not built on this rank)
     int64_t lo;       // exponent of scalar 0 (already shifted for commits)
     uint32_t len;
     bool commit_text;
@@ -407,10 +405,6 @@ struct ProofMsm {
 
 }  // namespace
 
-// Runs the prover.  d_in: canonical aL | aR | aO (3n Fr, may be null when !has_main) ;
-// d_rnd: canonical draws.  has_main = false computes only the hscProve part, with
-// d_rnd holding ys[Q] zs[Q] u v at the positions they have in the full draw order.
-// Outputs (host): proof bytes in record order.
 // Proof bytes from the G1 encodings (record order, 48 B each) and the Fr values (record order).
 static void assemble_proof(bool has_main, uint32_t M, const uint8_t* g48, const uint8_t* f32, uint8_t* out) {
     uint8_t* o = out;
@@ -430,17 +424,40 @@ __global__ void k_points_to_raw(const G1Affine* __restrict__ pts, uint32_t n, Fq
     out[2 * i + 1] = fp_from_mont(pts[i].y);
 }
 
-// out48[m] = compress(sum_r raw[r][m]),  raw laid out [world][nm] x 96 B.  When at most one rank
-// contributes (an MSM owned whole by one rank: everybody else holds the identity) the point is
-// already affine and is only re-encoded: no addition, no second inversion.  At most world-1 MSMs
-// are split between ranks and take the addition path.
-__global__ void k_fold_partials(const Fq* __restrict__ raw, uint32_t nm, uint32_t world, uint8_t* __restrict__ out48) {
-    const uint32_t m = blockIdx.x;   // one single-thread block per MSM: the Euclid inverse branches on the data
-    if (m >= nm || threadIdx.x != 0) return;
+// The fold of a sharded proof: `recs` holds one exchange record per rank (rec_bytes apart).
+//   blocks 0..nm-1   out48[m] = compress(sum_r raw[r][m]).  When at most one rank contributes (an MSM
+//                    owned whole by one rank: everybody else holds the identity) the point is already
+//                    affine and is only re-encoded: no addition, no second inversion.  At most world-1
+//                    MSMs are split between ranks and take the addition path.
+//   block nm         the field values (exactly one rank computes each; the others hold zeros, so the
+//                    bytes are OR-ed) and the status words (first violating index per MSM range = min
+//                    over the ranks that scanned it; encoding flag = OR).
+// Every rank that folds the same records reaches the same verdict.
+__global__ void k_fold_records(const uint8_t* __restrict__ recs, size_t rec_bytes, uint32_t nm, uint32_t nv, uint32_t world,
+                               size_t rec_vals, size_t rec_status, uint8_t* __restrict__ out, size_t out_vals, size_t out_status) {
+    const uint32_t m = blockIdx.x;
+    if (m == nm) {
+        const uint32_t nw = nv * 8;
+        for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) {
+            uint32_t v = 0;
+            for (uint32_t r = 0; r < world; ++r) v |= reinterpret_cast<const uint32_t*>(recs + r * rec_bytes + rec_vals)[i];
+            reinterpret_cast<uint32_t*>(out + out_vals)[i] = v;
+        }
+        for (uint32_t i = threadIdx.x; i < 3 * nm + 3; i += blockDim.x) {   // flags, then srsD (the same on every rank)
+            uint32_t v = i < 3 * nm ? 0xffffffffu : 0u;
+            for (uint32_t r = 0; r < world; ++r) {
+                const uint32_t w = reinterpret_cast<const uint32_t*>(recs + r * rec_bytes + rec_status)[i];
+                v = i < 3 * nm ? (w < v ? w : v) : (v | w);
+            }
+            reinterpret_cast<uint32_t*>(out + out_status)[i] = v;
+        }
+        return;
+    }
+    if (threadIdx.x != 0) return;   // one thread per MSM: the Euclid inverse branches on the data
     uint32_t contributors = 0;
     G1Affine only = G1Affine::inf();
     for (uint32_t r = 0; r < world; ++r) {
-        const Fq* p = raw + 2 * ((size_t)r * nm + m);
+        const Fq* p = reinterpret_cast<const Fq*>(recs + r * rec_bytes) + 2 * (size_t)m;
         if (!(p[0].is_zero() && p[1].is_zero())) {
             ++contributors;
             only.x = p[0];
@@ -449,158 +466,108 @@ __global__ void k_fold_partials(const Fq* __restrict__ raw, uint32_t nm, uint32_
     }
     if (contributors <= 1) {
         if (contributors) { only.x = fp_to_mont(only.x); only.y = fp_to_mont(only.y); }
-        g1_compress(only, out48 + (size_t)m * 48);
+        g1_compress(only, out + (size_t)m * 48);
         return;
     }
     G1XYZZ acc = G1XYZZ::inf();
     for (uint32_t r = 0; r < world; ++r) {
-        const Fq* p = raw + 2 * ((size_t)r * nm + m);
+        const Fq* p = reinterpret_cast<const Fq*>(recs + r * rec_bytes) + 2 * (size_t)m;
         G1Affine a;
         a.x = fp_to_mont(p[0]);
         a.y = fp_to_mont(p[1]);
         g1_madd(acc, a);  // (0,0) marks infinity and is skipped
     }
-    g1_compress(g1_to_affine_single(acc), out48 + (size_t)m * 48);
+    g1_compress(g1_to_affine_single(acc), out + (size_t)m * 48);
 }
 
-// Sharded proofs: every rank runs the Fr side in full and its equal run of the proof's MSM terms
-// (see prove_run); its output is then a "shard blob" = nm raw partial sums (96 B) followed by the
-// nF field values (32 B) in record order.  prove_combine folds the gathered blobs.
-int prove_combine(Ctx& cx, uint32_t M, bool has_main, uint32_t world, const uint8_t* blobs, uint8_t* out,
-                  uint64_t cap, uint64_t* written, const void* d_gathered) {
-    const uint32_t nm = has_main ? 4 * M + 7 : 4 * M + 2;
-    const uint32_t nF = has_main ? 2 * M + 5 : 2 * M + 2;
-    const uint64_t blob = (uint64_t)nm * 96 + (uint64_t)nF * 32;
-    const uint64_t need = (uint64_t)nm * 48 + (uint64_t)nF * 32;
+void prove_fold_enqueue(Ctx& cx, const ProveLayout& lay, uint32_t world, const uint8_t* d_records, uint8_t* d_out) {
+    (void)cx;
+    SONIC_LAUNCH(k_fold_records, lay.nm + 1, 64, 0, d_records, lay.rec_bytes(), lay.nm, lay.nv, world, lay.rec_vals(), lay.rec_status(),
+                 d_out, lay.out_vals(), lay.out_status());
+}
+
+// The status words decide, identically for every rank that holds the folded buffer, whether the call
+// succeeds: an encoding >= r, or the reference's `index` panic for the first MSM in record order with
+// a non-zero coefficient outside what the SRS holds (CommitmentScheme.hs:70-73; ascending exponents).
+int prove_finish(const ProveLayout& lay, const uint8_t* h_out, const uint8_t* rnd_host, uint8_t* proof, uint64_t cap,
+                 uint64_t* written) {
+    const uint64_t need = lay.proof_bytes();
     if (written) *written = need;
     if (cap < need) return fail(SONIC_ERR_BUFFER_TOO_SMALL, "proof needs %llu bytes", (unsigned long long)need);
-    // d_gathered: the partial sums of all ranks already in device memory, [world][nm] x 96 B (the
-    // output of the all-gather); then `blobs` is this rank's own blob and only supplies the field values
-    const Fq* d_raw_c = (const Fq*)d_gathered;
-    Fq* d_raw = nullptr;
-    if (!d_gathered) {
-        d_raw = cx.arena.get<Fq>(2 * (size_t)nm * world);
-        d_raw_c = d_raw;
-    }
-    for (uint32_t r = 0; r < world && !d_gathered; ++r)
-        SONIC_CUDA(cudaMemcpyAsync(d_raw + 2 * (size_t)r * nm, blobs + r * blob, (size_t)nm * 96, cudaMemcpyHostToDevice, cx.stream));
-    uint8_t* d_out = cx.arena.get<uint8_t>((size_t)nm * 48);
-    SONIC_LAUNCH(k_fold_partials, nm, 32, 0, d_raw_c, nm, world, d_out);
-    std::vector<uint8_t> g48((size_t)nm * 48);
-    SONIC_CUDA(cudaMemcpyAsync(g48.data(), d_out, g48.size(), cudaMemcpyDeviceToHost, cx.stream));
-    SONIC_CUDA(cudaStreamSynchronize(cx.stream));
-    assemble_proof(has_main, M, g48.data(), blobs + (size_t)nm * 96, out);
+    const uint32_t* st = reinterpret_cast<const uint32_t*>(h_out + lay.out_status());
+    const uint64_t d = (uint64_t)st[3 * (size_t)lay.nm + 1] | ((uint64_t)st[3 * (size_t)lay.nm + 2] << 32);
+    if (st[3 * (size_t)lay.nm]) return fail(SONIC_ERR_NONCANONICAL, "an Fr encoding is not a canonical residue (>= r)");
+    for (uint32_t i = 0; i < lay.nm; ++i)
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t v = st[3 * (size_t)i + k];
+            if (v == 0xffffffffu) continue;
+            // the flag holds the offending exponent biased by 2^30; which MSMs are commitments follows from the record order
+            const int64_t e = (int64_t)v - (int64_t)(1u << 30);
+            bool commit;
+            if (lay.has_main && i < 5) commit = i < 2;
+            else {
+                const uint32_t h = i - (lay.has_main ? 5u : 0u);
+                commit = h < 2 * lay.M ? (h % 2 == 0) : (h == 4 * lay.M + 1);
+            }
+            if (commit) {
+                if (e > 0) return fail(SONIC_ERR_SRS_TOO_SHORT, "commitPoly: gPositiveAlphaX is not long enough: %lld >= %llu", (long long)(e - 1), (unsigned long long)d);
+                return fail(SONIC_ERR_SRS_TOO_SHORT, "commitPoly: gNegativeAlphaX is not long enough: %lld >= %llu", (long long)((e < 0 ? -e : e) - 1), (unsigned long long)d);
+            }
+            if (e >= 0) return fail(SONIC_ERR_SRS_TOO_SHORT, "openPoly: gPositiveX is not long enough: %lld >= %llu", (long long)e, (unsigned long long)(d + 1));
+            return fail(SONIC_ERR_SRS_TOO_SHORT, "openPoly: gNegativeX is not long enough: %lld >= %llu", (long long)(-e - 1), (unsigned long long)d);
+        }
+    // field values in record order (Protocol.hs:28-38, Signature.hs:22-29): device values, then hscU, hscV from the draws
+    std::vector<uint8_t> f32((size_t)lay.nF * 32);
+    memcpy(f32.data(), h_out + lay.out_vals(), (size_t)lay.nv * 32);
+    memcpy(f32.data() + (size_t)lay.nv * 32, rnd_host + 32 * (6 + 2 * (size_t)lay.M), 64);
+    assemble_proof(lay.has_main, lay.M, h_out, f32.data(), proof);
     return SONIC_OK;
 }
 
-int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr* d_in, const Fr* d_rnd,
-              uint32_t M, bool has_main, uint32_t rank, uint32_t world, uint8_t* out, uint64_t cap, uint64_t* written,
-              void* d_partials_out) {
+// first non-zero scalar of s[a, b) -> its exponent (lo + index) biased by 2^30, atomicMin into *out
+__global__ void __launch_bounds__(256) k_first_violation(const Fr* __restrict__ s, uint32_t a, uint32_t b, int64_t lo, uint32_t* __restrict__ out) {
+    const uint32_t i = a + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b) return;
+    if (!s[i].is_zero()) atomicMin(out, (uint32_t)(lo + (int64_t)i + (int64_t)(1u << 30)));
+}
+
+int prove_enqueue(Ctx& cx, SrsRep& srs, const CircuitRep& circ_, const Fr* d_in, const Fr* d_rnd, uint32_t M, bool has_main,
+                  uint32_t rank, uint32_t world, uint8_t* d_result) {
+    const CircuitRep* circ = &circ_;
     const uint32_t n = (uint32_t)circ->n, Q = (uint32_t)circ->Q;
-    const int64_t d = (int64_t)srs->d;
-    const uint32_t nG = has_main ? 4 * M + 7 : 4 * M + 2;
-    const uint32_t nF = has_main ? 2 * M + 5 : 2 * M + 2;
+    const int64_t d = (int64_t)srs.d;
+    const ProveLayout lay(M, has_main);
     const bool sharded = world > 1;
-    const uint64_t need = (uint64_t)nG * (sharded ? 96 : 48) + (uint64_t)nF * 32;
-    if (written) *written = need;
-    if (cap < need) return fail(SONIC_ERR_BUFFER_TOO_SMALL, "output needs %llu bytes", (unsigned long long)need);
     Arena& ar = cx.arena;
     cudaStream_t st = cx.stream;
+    nvtxRangePushA("sonic.prove.poly");
     SONIC_CUDA(cudaEventRecord(cx.ev[4], st));
 
-    // ---- inputs to Montgomery form (flags non-canonical encodings) ---------------------------
-    const uint32_t nr = 2 * M + 8;
-    uint32_t* bad = ar.get<uint32_t>(1);
-    SONIC_CUDA(cudaMemsetAsync(bad, 0, 4, st));
-    Fr* rnd_m = ar.get<Fr>(nr);
-    fr_to_mont(cx, d_rnd, rnd_m, nr, bad);
-    Fr* in_m = nullptr;
-    if (has_main) {
-        in_m = ar.get<Fr>(3 * (size_t)n);
-        fr_to_mont(cx, d_in, in_m, 3 * (size_t)n, bad);
-    }
-
-    // ---- evaluation points and their power tables ---------------------------------------------
-    const uint32_t np = 2 * M + 5;
-    enum { PT_Y = 0, PT_Z = 1, PT_YZ = 2, PT_YJ = 3 };
-    const uint32_t PT_ZJ = 3 + M, PT_U = 3 + 2 * M, PT_V = 4 + 2 * M;
-    Fr* pts = ar.get<Fr>(2 * np);
-    SONIC_LAUNCH(k_prove_points, np, 32, 0, rnd_m, M, has_main ? 1 : 0, pts);
-    const uint64_t tl = std::max<uint64_t>(3 * (uint64_t)n + 8, 2 * (uint64_t)n + Q + 4);
-    Fr* tabs = ar.get<Fr>(2 * (size_t)np * tl);
-    pow_tables(cx, pts, 2 * np, tabs, tl, tl);
-    auto fwd = [&](uint32_t p) { return tabs + (size_t)p * tl; };
-    auto inv = [&](uint32_t p) { return tabs + (size_t)(np + p) * tl; };
-    // z also opens t(X,y), 7n+9 long
-    const uint64_t tlz = 7 * (uint64_t)n + 12;
-    Fr* ztabs = nullptr;
-    if (has_main) {
-        ztabs = ar.get<Fr>(2 * tlz);
-        Fr* zb = ar.get<Fr>(2);
-        SONIC_CUDA(cudaMemcpyAsync(zb, pts + PT_Z, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
-        SONIC_CUDA(cudaMemcpyAsync(zb + 1, pts + np + PT_Z, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
-        pow_tables(cx, zb, 2, ztabs, tlz, tlz);
-    }
-
-    // ---- s(X,y) for y (main) and every y_j ----------------------------------------------------
-    const uint32_t slen = 3 * n + 1;
-    const uint32_t nb = M + 1;  // batch: index 0 = y, 1..M = y_j
-    Fr* sxy_m = ar.get<Fr>((size_t)nb * slen);
-    Fr* sxy_c = ar.get<Fr>((size_t)nb * slen);
+    // ---- the result buffer (or this rank's exchange record): values zero, range flags "none", encoding flag clear
+    const uint32_t nm = lay.nm;
+    Fr* d_vals = reinterpret_cast<Fr*>(d_result + (sharded ? lay.rec_vals() : lay.out_vals()));
+    uint32_t* viol = reinterpret_cast<uint32_t*>(d_result + (sharded ? lay.rec_status() : lay.out_status()));
+    uint32_t* bad = viol + 3 * (size_t)nm;
+    SONIC_CUDA(cudaMemsetAsync(d_result, 0, sharded ? lay.rec_bytes() : lay.out_bytes(), st));
+    SONIC_CUDA(cudaMemsetAsync(viol, 0xff, 12 * (size_t)nm, st));
     {
-        std::vector<uint32_t> h_idx(2 * nb);
-        for (uint32_t b = 0; b < nb; ++b) {
-            const uint32_t p = b == 0 ? (uint32_t)PT_Y : (uint32_t)PT_YJ + (b - 1);
-            h_idx[b] = p;
-            h_idx[nb + b] = np + p;
-        }
-        uint32_t* d_idx = ar.get<uint32_t>(2 * nb);
-        SONIC_CUDA(cudaMemcpyAsync(d_idx, h_idx.data(), 8 * nb, cudaMemcpyHostToDevice, st));
-        if (circ->sparse) {
-            SparseView cl{circ->sp[0].col_ptr, circ->sp[0].row, circ->sp[0].cval}, cr{circ->sp[1].col_ptr, circ->sp[1].row, circ->sp[1].cval},
-                co{circ->sp[2].col_ptr, circ->sp[2].row, circ->sp[2].cval};
-            SONIC_LAUNCH(k_build_sxy_csc, dim3(div_up(n, 128), nb), 128, 0, cl, cr, co, n, tabs, tl, d_idx, d_idx + nb, sxy_m);
-        } else {
-            SONIC_LAUNCH(k_build_sxy, dim3(div_up(n, 128), nb), 128, 0, circ->wL(), circ->wR(), circ->wO(), n, Q, tabs, tl, d_idx, d_idx + nb, sxy_m);
-        }
-        fr_from_mont(cx, sxy_m, sxy_c, (size_t)nb * slen);
+        const uint32_t dw[2] = {(uint32_t)srs.d, (uint32_t)(srs.d >> 32)};   // 8 pageable bytes: staged before the call returns
+        SONIC_CUDA(cudaMemcpyAsync(bad + 1, dw, 8, cudaMemcpyHostToDevice, st));
     }
-    auto sxy = [&](uint32_t b) { Window w; w.mont = sxy_m + (size_t)b * slen; w.canon = sxy_c + (size_t)b * slen; w.lo = -(int64_t)n; w.len = slen; return w; };
-
-    // ---- s(u,Y) -------------------------------------------------------------------------------
-    Window suy;
-    suy.len = 2 * n + Q + 1;
-    suy.lo = -(int64_t)n;
-    suy.mont = ar.get<Fr>(suy.len);
-    suy.canon = ar.get<Fr>(suy.len);
-    SONIC_LAUNCH(k_build_suy_pm, div_up(2 * n + 1, 256), 256, 0, fwd(PT_U), n, Q, suy.mont);
-    {
-        Fr* part = ar.get<Fr>((size_t)Q * SUY_PARTS);
-        if (circ->sparse) {
-            SparseView rl{circ->sp[0].row_ptr, circ->sp[0].col, circ->sp[0].val}, rr{circ->sp[1].row_ptr, circ->sp[1].col, circ->sp[1].val},
-                ro{circ->sp[2].row_ptr, circ->sp[2].col, circ->sp[2].val};
-            SONIC_LAUNCH(k_build_suy_dot_csr, dim3(SUY_PARTS, Q), 256, 0, rl, rr, ro, n, fwd(PT_U), inv(PT_U), part);
-        } else {
-            SONIC_LAUNCH(k_build_suy_dot, dim3(SUY_PARTS, Q), 256, 0, circ->wL(), circ->wR(), circ->wO(), n, fwd(PT_U), inv(PT_U), part);
-        }
-        SONIC_LAUNCH(k_build_suy_fin, div_up(Q, 64), 64, 0, part, n, Q, suy.mont);
-    }
-    fr_from_mont(cx, suy.mont, suy.canon, suy.len);
 
     // ---- which MSMs does this rank sum? -------------------------------------------------------------
     // The shapes of the proof's MSMs (exponent of scalar 0 and length, record order) depend only on
     // n, Q, M and d, so the dealing is known before any polynomial exists, and a rank of a sharded
-    // proof can skip what feeds only other ranks' MSMs: t(X,y) (two forward and one inverse NTT)
-    // unless it owns part of prT / prWt, and the quotient pass of openings it owns no part of.
-    // Every rank still evaluates everything that goes into the proof as a field value.
+    // proof builds only what feeds its own MSMs (below).
     // Sharding: the (clipped) exponent windows of all MSMs, concatenated in
-    // record order, are cut into `world` equal runs of terms.  A rank so owns a few whole MSMs plus
+    // record order, are cut into `world` runs of terms.  A rank so owns a few whole MSMs plus
     // at most two partial ones -- sorting, bucket reduction and the tail shrink with the rank count,
     // the loads differ by at most one term, and at most world-1 MSMs are split (their partial sums
     // meet in the fold).  A deterministic function of the sizes: all ranks agree.  Mirrored by
     // sonic_b200/dist.py:deal_terms.
     struct Shape { int64_t lo; uint32_t len; };
     std::vector<Shape> shape;
+    const uint32_t slen = 3 * n + 1;
     {
         const int64_t nn = (int64_t)n;
         const uint32_t rlen = 3 * n + 5, tlen = 7 * n + 9, ulen = 2 * n + Q + 1;
@@ -618,7 +585,9 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
         shape.push_back({-nn, ulen});                  // C
     }
     const uint32_t nshape = (uint32_t)shape.size();
+    if (nshape != nm) return fail(SONIC_ERR_INVALID_ARG, "internal: MSM list does not match the proof layout");
     std::vector<int64_t> piece_lo(nshape), piece_hi(nshape);  // this rank's part [lo, hi) of every window, as exponents
+    std::vector<uint32_t> first_owner(nshape, 0);             // lowest rank holding terms of the MSM (0 for an empty window)
     {
         // clipped windows and their positions in the concatenation
         std::vector<int64_t> clo(nshape);
@@ -668,34 +637,183 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
             const uint64_t b = run_hi > pos[i] ? std::min(run_hi - pos[i], span) : 0;
             piece_lo[i] = clo[i] + (int64_t)a;
             piece_hi[i] = clo[i] + (int64_t)b;
+            for (uint32_t r = 0; r < W_; ++r)
+                if (std::min(bound[r + 1], pos[i + 1]) > std::max(bound[r], pos[i])) { first_owner[i] = r; break; }
         }
     }
+    // `mine(i)`: this rank builds the scalar vector of MSM i (it sums part of it, or nobody does and rank 0
+    // stands in so that the range scan of CommitmentScheme.hs:70-73 still happens); `lead(i)`: this rank
+    // also contributes the field value that opening i yields.
     auto owns = [&](uint32_t i) { return piece_hi[i] > piece_lo[i]; };
+    auto lead = [&](uint32_t i) { return first_owner[i] == rank; };
+    auto mine = [&](uint32_t i) { return owns(i) || lead(i); };
     const uint32_t mbase = has_main ? 5u : 0u;  // record index of S_1
-    const bool need_t = has_main && (owns(1) || owns(4));
+    auto iS = [&](uint32_t j) { return mbase + 2 * j; };
+    auto iW = [&](uint32_t j) { return mbase + 2 * j + 1; };
+    auto iWp = [&](uint32_t j) { return mbase + 2 * M + 2 * j; };
+    auto iQ = [&](uint32_t j) { return mbase + 2 * M + 2 * j + 1; };
+    const uint32_t iQv = mbase + 4 * M, iC = mbase + 4 * M + 1;
+
+    // ---- what has to exist on this rank -----------------------------------------------------------------
+    // Everything below is demand-driven: a vector, a power table or an opening is built only if one of
+    // this rank's MSMs (or a field value it leads) needs it.  With one rank everything is needed.
+    const bool need_t = has_main && (mine(1) || mine(4));
+    const bool lead_s = has_main && lead(1);                       // prS = s(z, y) comes from the rank that leads prT
+    const bool need_rx1 = has_main && (mine(0) || mine(2) || mine(3) || need_t);
+    const bool need_s0 = need_t || lead_s;
+    std::vector<char> need_sj(M, 0);
+    bool need_suy = mine(iQv) || mine(iC);
+    for (uint32_t j = 0; j < M; ++j) {
+        need_sj[j] = mine(iS(j)) || mine(iW(j)) || mine(iWp(j));
+        need_suy = need_suy || mine(iQ(j));
+    }
+
+    // ---- inputs to Montgomery form (flags non-canonical encodings; every rank checks) ---------------------
+    const uint32_t nr = 2 * M + 8;
+    Fr* rnd_m = ar.get<Fr>(nr);
+    fr_to_mont(cx, d_rnd, rnd_m, nr, bad);
+    Fr* in_m = nullptr;
+    if (has_main) {
+        in_m = ar.get<Fr>(3 * (size_t)n);
+        fr_to_mont(cx, d_in, in_m, 3 * (size_t)n, bad);
+    }
+
+    // ---- evaluation points and their power tables ---------------------------------------------
+    const uint32_t np = 2 * M + 5;
+    enum { PT_Y = 0, PT_Z = 1, PT_YZ = 2, PT_YJ = 3 };
+    const uint32_t PT_ZJ = 3 + M, PT_U = 3 + 2 * M, PT_V = 4 + 2 * M;
+    std::vector<char> need_pt(np, 0);
+    bool need_zlong = false;   // z also opens t(X,y), 7n+9 long
+    if (has_main) {
+        if (need_s0 || need_t) need_pt[PT_Y] = 1;
+        if (mine(4)) need_zlong = true;
+        if (mine(2) || lead_s || need_zlong) need_pt[PT_Z] = 1;
+        if (mine(3)) need_pt[PT_YZ] = 1;
+    }
+    for (uint32_t j = 0; j < M; ++j) {
+        if (need_sj[j] || mine(iQ(j))) need_pt[PT_YJ + j] = 1;
+        if (mine(iW(j))) need_pt[PT_ZJ + j] = 1;
+        if (mine(iWp(j))) need_pt[PT_U] = 1;
+    }
+    if (need_suy) need_pt[PT_U] = 1;
+    if (mine(iQv)) need_pt[PT_V] = 1;
+    Fr* pts = ar.get<Fr>(2 * np);
+    const uint64_t tl = std::max<uint64_t>(3 * (uint64_t)n + 8, 2 * (uint64_t)n + Q + 4);
+    Fr* tabs = ar.get<Fr>(2 * (size_t)np * tl);
+    {
+        std::vector<uint32_t> sel_p, sel_t;
+        for (uint32_t p = 0; p < np; ++p)
+            if (need_pt[p]) { sel_p.push_back(p); }
+        for (uint32_t p : sel_p) sel_t.push_back(p);
+        for (uint32_t p : sel_p) sel_t.push_back(np + p);
+        if (!sel_p.empty()) {
+            uint32_t* d_sel = ar.get<uint32_t>(3 * sel_p.size());
+            std::vector<uint32_t> h(sel_p);
+            h.insert(h.end(), sel_t.begin(), sel_t.end());
+            SONIC_CUDA(cudaMemcpyAsync(d_sel, h.data(), 4 * h.size(), cudaMemcpyHostToDevice, st));
+            SONIC_LAUNCH(k_prove_points, (unsigned)sel_p.size(), 32, 0, rnd_m, M, has_main ? 1 : 0, d_sel, pts);
+            pow_tables(cx, pts, (int)sel_t.size(), tabs, tl, tl, d_sel + sel_p.size());
+        }
+    }
+    auto fwd = [&](uint32_t p) { return tabs + (size_t)p * tl; };
+    auto inv = [&](uint32_t p) { return tabs + (size_t)(np + p) * tl; };
+    const uint64_t tlz = 7 * (uint64_t)n + 12;
+    const Fr* zf = fwd(PT_Z);
+    const Fr* zi = inv(PT_Z);
+    if (need_zlong) {
+        Fr* ztabs = ar.get<Fr>(2 * tlz);
+        Fr* zb = ar.get<Fr>(2);
+        SONIC_CUDA(cudaMemcpyAsync(zb, pts + PT_Z, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+        SONIC_CUDA(cudaMemcpyAsync(zb + 1, pts + np + PT_Z, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+        pow_tables(cx, zb, 2, ztabs, tlz, tlz);
+        zf = ztabs;
+        zi = ztabs + tlz;
+    }
+
+    // ---- s(X,y) for y (main) and the y_j this rank needs ----------------------------------------------
+    const uint32_t nb = M + 1;  // batch slots: 0 = y, 1..M = y_j
+    Fr* sxy_m = ar.get<Fr>((size_t)nb * slen);
+    Fr* sxy_c = ar.get<Fr>((size_t)nb * slen);
+    {
+        std::vector<uint32_t> slots;
+        if (need_s0) slots.push_back(0);
+        for (uint32_t j = 0; j < M; ++j) if (need_sj[j]) slots.push_back(1 + j);
+        const uint32_t ns = (uint32_t)slots.size();
+        if (ns) {
+            std::vector<uint32_t> h_idx(3 * (size_t)ns);
+            for (uint32_t k = 0; k < ns; ++k) {
+                const uint32_t b = slots[k];
+                const uint32_t p = b == 0 ? (uint32_t)PT_Y : (uint32_t)PT_YJ + (b - 1);
+                h_idx[k] = p;
+                h_idx[ns + k] = np + p;
+                h_idx[2 * ns + k] = b;
+            }
+            uint32_t* d_idx = ar.get<uint32_t>(3 * (size_t)ns);
+            SONIC_CUDA(cudaMemcpyAsync(d_idx, h_idx.data(), 12 * (size_t)ns, cudaMemcpyHostToDevice, st));
+            if (circ->sparse) {
+                SparseView cl{circ->sp[0].col_ptr, circ->sp[0].row, circ->sp[0].cval}, cr{circ->sp[1].col_ptr, circ->sp[1].row, circ->sp[1].cval},
+                    co{circ->sp[2].col_ptr, circ->sp[2].row, circ->sp[2].cval};
+                SONIC_LAUNCH(k_build_sxy_csc, dim3(div_up(n, 128), ns), 128, 0, cl, cr, co, n, tabs, tl, d_idx, d_idx + ns, d_idx + 2 * ns, sxy_m);
+            } else {
+                SONIC_LAUNCH(k_build_sxy, dim3(div_up(n, 128), ns), 128, 0, circ->wL(), circ->wR(), circ->wO(), n, Q, tabs, tl, d_idx, d_idx + ns, d_idx + 2 * ns, sxy_m);
+            }
+            // canonical copies only where the vector itself is committed to (S_j); runs of adjacent slots in one launch
+            for (uint32_t k = 0; k < ns;) {
+                if (slots[k] == 0 || !mine(iS(slots[k] - 1))) { ++k; continue; }
+                uint32_t e = k + 1;
+                while (e < ns && slots[e] == slots[e - 1] + 1 && mine(iS(slots[e] - 1))) ++e;
+                fr_from_mont(cx, sxy_m + (size_t)slots[k] * slen, sxy_c + (size_t)slots[k] * slen, (size_t)(e - k) * slen);
+                k = e;
+            }
+        }
+    }
+    auto sxy = [&](uint32_t b) { Window w; w.mont = sxy_m + (size_t)b * slen; w.canon = sxy_c + (size_t)b * slen; w.lo = -(int64_t)n; w.len = slen; return w; };
+
+    // ---- s(u,Y) -------------------------------------------------------------------------------
+    Window suy;
+    suy.len = 2 * n + Q + 1;
+    suy.lo = -(int64_t)n;
+    if (need_suy) {
+        suy.mont = ar.get<Fr>(suy.len);
+        suy.canon = ar.get<Fr>(suy.len);
+        SONIC_LAUNCH(k_build_suy_pm, div_up(2 * n + 1, 256), 256, 0, fwd(PT_U), n, Q, suy.mont);
+        Fr* part = ar.get<Fr>((size_t)Q * SUY_PARTS);
+        if (circ->sparse) {
+            SparseView rl{circ->sp[0].row_ptr, circ->sp[0].col, circ->sp[0].val}, rr{circ->sp[1].row_ptr, circ->sp[1].col, circ->sp[1].val},
+                ro{circ->sp[2].row_ptr, circ->sp[2].col, circ->sp[2].val};
+            SONIC_LAUNCH(k_build_suy_dot_csr, dim3(SUY_PARTS, Q), 256, 0, rl, rr, ro, n, fwd(PT_U), inv(PT_U), part);
+        } else {
+            SONIC_LAUNCH(k_build_suy_dot, dim3(SUY_PARTS, Q), 256, 0, circ->wL(), circ->wR(), circ->wO(), n, fwd(PT_U), inv(PT_U), part);
+        }
+        SONIC_LAUNCH(k_build_suy_fin, div_up(Q, 64), 64, 0, part, n, Q, suy.mont);
+        if (mine(iC)) fr_from_mont(cx, suy.mont, suy.canon, suy.len);
+    }
 
     // ---- r'(X,1), t(X,y) ------------------------------------------------------------------------
     Window rx1, txy;
-    if (has_main) {
-        rx1.len = 3 * n + 5;
-        rx1.lo = -2 * (int64_t)n - 4;
-        txy.len = 7 * n + 9;
-        txy.lo = -4 * (int64_t)n - 8;
+    rx1.len = 3 * n + 5;
+    rx1.lo = -2 * (int64_t)n - 4;
+    txy.len = 7 * n + 9;
+    txy.lo = -4 * (int64_t)n - 8;
+    if (need_rx1) {
         uint32_t logL = 1;
         while ((1ull << logL) < txy.len) ++logL;
-        const uint64_t L = 1ull << logL;
+        const uint64_t L = need_t ? 1ull << logL : rx1.len;
         Fr* A = ar.get<Fr>(L);
-        Fr* B = ar.get<Fr>(L);
-        SONIC_CUDA(cudaMemsetAsync(A, 0, L * sizeof(Fr), st));
-        SONIC_CUDA(cudaMemsetAsync(B, 0, L * sizeof(Fr), st));
+        if (need_t) SONIC_CUDA(cudaMemsetAsync(A, 0, L * sizeof(Fr), st));
         SONIC_LAUNCH(k_build_r, div_up(rx1.len, 256), 256, 0, in_m, in_m + n, in_m + 2 * (size_t)n, rnd_m, n, A);
-        rx1.mont = ar.get<Fr>(rx1.len);
-        rx1.canon = ar.get<Fr>(rx1.len);
-        SONIC_CUDA(cudaMemcpyAsync(rx1.mont, A, rx1.len * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
-        fr_from_mont(cx, rx1.mont, rx1.canon, rx1.len);
-        txy.mont = nullptr;
-        txy.canon = nullptr;
+        rx1.mont = A;
         if (need_t) {
+            rx1.mont = ar.get<Fr>(rx1.len);
+            SONIC_CUDA(cudaMemcpyAsync(rx1.mont, A, rx1.len * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+        }
+        if (mine(0)) {
+            rx1.canon = ar.get<Fr>(rx1.len);
+            fr_from_mont(cx, rx1.mont, rx1.canon, rx1.len);
+        }
+        if (need_t) {
+            Fr* B = ar.get<Fr>(L);
+            SONIC_CUDA(cudaMemsetAsync(B, 0, L * sizeof(Fr), st));
             SONIC_LAUNCH(k_build_rs, div_up(4 * n + 5, 256), 256, 0, rx1.mont, sxy_m, fwd(PT_Y), inv(PT_Y), n, B);
             NttPlan plan = ntt_prepare(cx, logL);
             ntt_forward(plan, A);
@@ -704,51 +822,55 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
             ntt_inverse(plan, A);
             SONIC_LAUNCH(k_t_fix, 1, 32, 0, A, circ->cs(), fwd(PT_Y), n, Q);
             txy.mont = A;
-            txy.canon = ar.get<Fr>(txy.len);
-            fr_from_mont(cx, txy.mont, txy.canon, txy.len);
+            if (mine(1)) {
+                txy.canon = ar.get<Fr>(txy.len);
+                fr_from_mont(cx, txy.mont, txy.canon, txy.len);
+            }
         }
     }
 
     // ---- openings: values and quotient vectors --------------------------------------------------
-    // values (canonical) collected in one array; quotients in their own buffers
+    // a value goes straight into its slot of the result buffer when this rank leads the opening
+    // (record order: prA prB prS | s_j | s'_j), else into scratch
     std::vector<OpenJob> ojobs;
-    Fr* vals = ar.get<Fr>(3 * (size_t)M + 8);
-    uint32_t nvals = 0;
+    Fr* scratch = ar.get<Fr>(3 * (size_t)M + 8);
+    uint32_t nscratch = 0;
     struct Quot { Fr* q; int64_t lo; uint32_t len; };
-    auto add_open = [&](const Window& f, const Fr* pz, const Fr* pzi, bool want_q, uint32_t* val_slot) -> Quot {
+    auto add_open = [&](const Window& f, const Fr* pz, const Fr* pzi, bool want_q, Fr* value_slot) -> Quot {
+        Quot qt{nullptr, f.lo, f.len - 1};
+        if (!want_q && !value_slot) return qt;
         OpenJob jb;
         jb.f = f.mont;
         jb.pz = pz;
         jb.pzi = pzi;
         jb.q_canon = want_q ? ar.get<Fr>(f.len) : nullptr;
-        jb.value_canon = vals + nvals;
-        *val_slot = nvals++;
+        jb.value_canon = value_slot ? value_slot : scratch + nscratch++;
         jb.len = f.len;
         jb.lo = (int32_t)f.lo;
         jb.z_is_zero = 0;
         jb.pad = 0;
         ojobs.push_back(jb);
-        return Quot{jb.q_canon, f.lo, f.len - 1};
+        qt.q = jb.q_canon;
+        return qt;
     };
-    uint32_t v_a = 0, v_b = 0, v_t = 0, v_s = 0, v_qv = 0;
-    std::vector<uint32_t> v_sj(M), v_spj(M), v_wpj(M);
-    Quot q_a{}, q_b{}, q_t{}, q_v{};
+    const uint32_t vbase = has_main ? 3u : 0u;
+    Quot q_a{nullptr, rx1.lo, rx1.len - 1}, q_b{nullptr, rx1.lo, rx1.len - 1}, q_t{nullptr, txy.lo, txy.len - 1}, q_v{};
     std::vector<Quot> q_wj(M), q_wpj(M), q_qj(M);
     if (has_main) {
-        q_a = add_open(rx1, ztabs, ztabs + tlz, owns(2), &v_a);              // Protocol.hs:79
-        q_b = add_open(rx1, fwd(PT_YZ), inv(PT_YZ), owns(3), &v_b);         // Protocol.hs:80
-        if (need_t) q_t = add_open(txy, ztabs, ztabs + tlz, owns(4), &v_t);  // Protocol.hs:81 (t(z,y) itself is not a proof field)
-        else q_t = Quot{nullptr, txy.lo, txy.len - 1};
-        add_open(sxy(0), ztabs, ztabs + tlz, false, &v_s);                   // Protocol.hs:83
+        q_a = add_open(rx1, zf, zi, mine(2), lead(2) ? d_vals + 0 : nullptr);                    // Protocol.hs:79
+        q_b = add_open(rx1, fwd(PT_YZ), inv(PT_YZ), mine(3), lead(3) ? d_vals + 1 : nullptr);    // Protocol.hs:80
+        q_t = add_open(txy, zf, zi, mine(4), nullptr);      // Protocol.hs:81 (t(z,y) itself is not a proof field)
+        if (lead_s) add_open(sxy(0), zf, zi, false, d_vals + 2);                                 // Protocol.hs:83
     }
     for (uint32_t j = 0; j < M; ++j) {
-        q_wj[j] = add_open(sxy(1 + j), fwd(PT_ZJ + j), inv(PT_ZJ + j), owns(mbase + 2 * j + 1), &v_sj[j]);            // Signature.hs:43
-        q_wpj[j] = add_open(sxy(1 + j), fwd(PT_U), inv(PT_U), owns(mbase + 2 * M + 2 * j), &v_wpj[j]);                // Signature.hs:54
-        q_qj[j] = add_open(suy, fwd(PT_YJ + j), inv(PT_YJ + j), owns(mbase + 2 * M + 2 * j + 1), &v_spj[j]);          // Signature.hs:55
+        q_wj[j] = add_open(sxy(1 + j), fwd(PT_ZJ + j), inv(PT_ZJ + j), mine(iW(j)), lead(iW(j)) ? d_vals + vbase + j : nullptr);     // Signature.hs:43
+        q_wpj[j] = add_open(sxy(1 + j), fwd(PT_U), inv(PT_U), mine(iWp(j)), nullptr);                                                // Signature.hs:54
+        q_qj[j] = add_open(suy, fwd(PT_YJ + j), inv(PT_YJ + j), mine(iQ(j)), lead(iQ(j)) ? d_vals + vbase + M + j : nullptr);        // Signature.hs:55
     }
-    q_v = add_open(suy, fwd(PT_V), inv(PT_V), owns(mbase + 4 * M), &v_qv);                  // Signature.hs:63
+    q_v = add_open(suy, fwd(PT_V), inv(PT_V), mine(iQv), nullptr);                                                                   // Signature.hs:63
     open_batch(cx, ojobs);
     SONIC_CUDA(cudaEventRecord(cx.ev[5], st));
+    nvtxRangePop();
 
     // ---- the proof's MSMs, in record order -----------------------------------------------------
     std::vector<ProofMsm> pm;
@@ -761,44 +883,57 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
         opening(q_b);             // prWb
         opening(q_t);             // prWt
     }
-    for (uint32_t j = 0; j < M; ++j) { commit(sxy(1 + j), d); opening(q_wj[j]); }      // hscS   Signature.hs:42-43
+    for (uint32_t j = 0; j < M; ++j) {   // hscS   Signature.hs:42-43
+        Window w = sxy(1 + j);
+        if (!mine(iS(j))) w.canon = nullptr;
+        commit(w, d);
+        opening(q_wj[j]);
+    }
     for (uint32_t j = 0; j < M; ++j) { opening(q_wpj[j]); opening(q_qj[j]); }          // hscW   Signature.hs:54-55
     opening(q_v);                                                                       // hscQv  Signature.hs:63
     commit(suy, d);                                                                     // hscC   Signature.hs:52
-
-    // range / hole checks: first non-zero scalar outside what the SRS holds, per MSM
-    const uint32_t nm = (uint32_t)pm.size();
-    uint32_t* viol = ar.get<uint32_t>(3 * (size_t)nm);
-    SONIC_CUDA(cudaMemsetAsync(viol, 0xff, 12 * (size_t)nm, st));
-    std::vector<MsmJob> jobs(nm);
-    std::vector<int64_t> slice_lo(nm, 0);
-    // the dealing was fixed from the shapes alone (above); the MSM list must agree with them
-    if (nm != nshape) return fail(SONIC_ERR_INVALID_ARG, "internal: MSM list does not match its shape table");
+    if ((uint32_t)pm.size() != nshape) return fail(SONIC_ERR_INVALID_ARG, "internal: MSM list does not match its shape table");
     for (uint32_t i = 0; i < nm; ++i)
         if (pm[i].lo != shape[i].lo || pm[i].len != shape[i].len) return fail(SONIC_ERR_INVALID_ARG, "internal: MSM %u does not match its shape", i);
-    struct Rng { int64_t a, b; };
-    std::vector<Rng> rngs(3 * (size_t)nm, Rng{0, 0});
+
+    // range / hole checks: first non-zero scalar outside what the SRS holds, per MSM, by the ranks that
+    // built the vector (the fold takes the minimum, so every rank reaches the same verdict)
+    std::vector<MsmJob> jobs(nm);
+    std::vector<int64_t> slice_lo(nm, 0);
     for (uint32_t i = 0; i < nm; ++i) {
         const ProofMsm& m = pm[i];
         const int64_t lo = m.lo, hi = m.lo + (int64_t)m.len;
-        Rng* r = &rngs[3 * (size_t)i];
+        struct Rng { int64_t a, b; } r[3] = {{0, 0}, {0, 0}, {0, 0}};
         if (lo < -d) r[0] = {lo, std::min(hi, -d)};
         if (m.family == SONIC_FAMILY_ALPHA && lo <= 0 && 0 < hi) r[1] = {0, 1};
         if (hi > d + 1) r[2] = {std::max(lo, d + 1), hi};
         for (int k = 0; k < 3; ++k) {
             if (r[k].b > r[k].a && m.scal) {
                 const uint32_t a = (uint32_t)(r[k].a - lo), b = (uint32_t)(r[k].b - lo);
-                SONIC_LAUNCH(k_first_nonzero_job, div_up(b - a, 256), 256, 0, m.scal, a, b, viol + 3 * (size_t)i + k);
+                SONIC_LAUNCH(k_first_violation, div_up(b - a, 256), 256, 0, m.scal, a, b, lo, viol + 3 * (size_t)i + k);
             }
         }
         // the part of this window inside the rank's run of terms (the whole clipped window when not sharded)
         const int64_t clo = piece_lo[i], chi = piece_hi[i];
         slice_lo[i] = clo;
-        jobs[i].point_base = (uint32_t)srs->index(m.family, clo);
+        jobs[i].point_base = 0;
         jobs[i].n = (uint32_t)(chi - clo);
-        // scalar_off is relative to one base pointer: use the arena base of the first job
         jobs[i].scalar_off = 0;
         jobs[i].pad = 0;
+    }
+    // ---- bases: the full-range window tables, else tables restricted to this circuit size, else none ----
+    const G1Affine* d_points = srs.points;
+    MsmTables tables = srs.tables;
+    bool restricted = false;
+    if (srs.tables.c == 0 && srs.rt.points) {
+        restricted = true;
+        for (uint32_t i = 0; i < nm && restricted; ++i)
+            if (jobs[i].n && srs.rt.find(pm[i].family, slice_lo[i], jobs[i].n) < 0) restricted = false;
+        if (restricted) { d_points = srs.rt.points; tables = srs.rt.tables; }
+    }
+    for (uint32_t i = 0; i < nm; ++i) {
+        if (!jobs[i].n) continue;
+        jobs[i].point_base = restricted ? (uint32_t)srs.rt.find(pm[i].family, slice_lo[i], jobs[i].n) : (uint32_t)srs.index(pm[i].family, slice_lo[i]);
     }
     // all scalar vectors live in the arena; express them as offsets from the lowest address
     const Fr* sbase = nullptr;
@@ -809,89 +944,43 @@ int prove_run(Ctx& cx, const sonic_srs* srs, const sonic_circuit* circ, const Fr
     }
     for (uint32_t i = 0; i < nm; ++i)
         if (jobs[i].n) jobs[i].scalar_off = (uint32_t)((pm[i].scal - sbase) + (slice_lo[i] - pm[i].lo));
-    G1Affine* d_aff = ar.get<G1Affine>(nm);
-    uint8_t* d_comp = ar.get<uint8_t>((size_t)nm * 48);
+    nvtxRangePushA("sonic.prove.msm");
     if (sharded) {
-        // only this rank's MSMs (whole or partial) enter the pipeline; the others contribute the identity
+        // only this rank's MSMs (whole or partial) enter the pipeline; the others contribute the identity (zeros)
+        G1Affine* d_aff = ar.get<G1Affine>(nm);
         SONIC_CUDA(cudaMemsetAsync(d_aff, 0, (size_t)nm * sizeof(G1Affine), st));
-        std::vector<uint32_t> mine;
-        for (uint32_t i = 0; i < nm; ++i) if (jobs[i].n > 0) mine.push_back(i);
-        G1Affine* d_mine = ar.get<G1Affine>(mine.size() ? mine.size() : 1);
-        for (size_t first = 0; first < mine.size(); first += MSM_MAX_JOBS) {
-            const size_t cnt = std::min<size_t>(MSM_MAX_JOBS, mine.size() - first);
+        std::vector<uint32_t> own;
+        for (uint32_t i = 0; i < nm; ++i) if (jobs[i].n > 0) own.push_back(i);
+        G1Affine* d_mine = ar.get<G1Affine>(own.size() ? own.size() : 1);
+        for (size_t first = 0; first < own.size(); first += MSM_MAX_JOBS) {
+            const size_t cnt = std::min<size_t>(MSM_MAX_JOBS, own.size() - first);
             std::vector<MsmJob> part;
-            for (size_t k = 0; k < cnt; ++k) part.push_back(jobs[mine[first + k]]);
-            msm_run(cx, srs->points, srs->tables, (const uint32_t*)sbase, part, d_mine + first, nullptr);
+            for (size_t k = 0; k < cnt; ++k) part.push_back(jobs[own[first + k]]);
+            msm_run(cx, d_points, tables, (const uint32_t*)sbase, part, d_mine + first, nullptr);
         }
-        for (size_t k = 0; k < mine.size(); ++k)
-            SONIC_CUDA(cudaMemcpyAsync(d_aff + mine[k], d_mine + k, sizeof(G1Affine), cudaMemcpyDeviceToDevice, st));
+        // runs of consecutive record indices move in one copy
+        for (size_t k = 0; k < own.size();) {
+            size_t e = k + 1;
+            while (e < own.size() && own[e] == own[e - 1] + 1) ++e;
+            SONIC_CUDA(cudaMemcpyAsync(d_aff + own[k], d_mine + k, (e - k) * sizeof(G1Affine), cudaMemcpyDeviceToDevice, st));
+            k = e;
+        }
+        SONIC_LAUNCH(k_points_to_raw, div_up(nm, 64), 64, 0, d_aff, nm, reinterpret_cast<Fq*>(d_result));
     } else {
         for (uint32_t first = 0; first < nm; first += MSM_MAX_JOBS) {
             const uint32_t cnt = std::min<uint32_t>(MSM_MAX_JOBS, nm - first);
             std::vector<MsmJob> part(jobs.begin() + first, jobs.begin() + first + cnt);
-            msm_run(cx, srs->points, srs->tables, (const uint32_t*)sbase, part, d_aff + first, d_comp + (size_t)first * 48);
+            msm_run(cx, d_points, tables, (const uint32_t*)sbase, part, nullptr, d_result + (size_t)first * 48);
         }
     }
-
-    // ---- results to the host ---------------------------------------------------------------------
-    std::vector<uint8_t> h_comp((size_t)nm * (sharded ? 96 : 48));
-    std::vector<Fr> h_vals(nvals ? nvals : 1);
-    std::vector<uint32_t> h_viol(3 * (size_t)nm);
-    std::vector<Fr> h_rnd(nr);
-    uint32_t h_bad = 0;
-    if (sharded) {
-        Fq* d_raw = ar.get<Fq>(2 * (size_t)nm);
-        SONIC_LAUNCH(k_points_to_raw, div_up(nm, 64), 64, 0, d_aff, nm, d_raw);
-        SONIC_CUDA(cudaMemcpyAsync(h_comp.data(), d_raw, h_comp.size(), cudaMemcpyDeviceToHost, st));
-        if (d_partials_out)  // exchange buffer of the caller (e.g. the input of an NCCL all-gather)
-            SONIC_CUDA(cudaMemcpyAsync(d_partials_out, d_raw, h_comp.size(), cudaMemcpyDeviceToDevice, st));
-    } else {
-        SONIC_CUDA(cudaMemcpyAsync(h_comp.data(), d_comp, h_comp.size(), cudaMemcpyDeviceToHost, st));
-    }
-    SONIC_CUDA(cudaMemcpyAsync(h_vals.data(), vals, nvals * sizeof(Fr), cudaMemcpyDeviceToHost, st));
-    SONIC_CUDA(cudaMemcpyAsync(h_viol.data(), viol, h_viol.size() * 4, cudaMemcpyDeviceToHost, st));
-    SONIC_CUDA(cudaMemcpyAsync(h_rnd.data(), d_rnd, nr * sizeof(Fr), cudaMemcpyDeviceToHost, st));
-    SONIC_CUDA(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, st));
-    SONIC_CUDA(cudaStreamSynchronize(st));
-    msm_collect_timing(cx);
-    {
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, cx.ev[4], cx.ev[5]) == cudaSuccess) cx.timing_ms["poly"] = ms;
-    }
-    if (h_bad) return fail(SONIC_ERR_NONCANONICAL, "an Fr encoding is not a canonical residue (>= r)");
-    for (uint32_t i = 0; i < nm; ++i)
-        for (int k = 0; k < 3; ++k) {
-            const uint32_t v = h_viol[3 * (size_t)i + k];
-            if (v == 0xffffffffu) continue;
-            const int64_t e = pm[i].lo + (int64_t)v;
-            const uint64_t dd = srs->d;
-            if (pm[i].commit_text) {
-                if (e > 0) return fail(SONIC_ERR_SRS_TOO_SHORT, "commitPoly: gPositiveAlphaX is not long enough: %lld >= %llu", (long long)(e - 1), (unsigned long long)dd);
-                return fail(SONIC_ERR_SRS_TOO_SHORT, "commitPoly: gNegativeAlphaX is not long enough: %lld >= %llu", (long long)((e < 0 ? -e : e) - 1), (unsigned long long)dd);
-            }
-            if (e >= 0) return fail(SONIC_ERR_SRS_TOO_SHORT, "openPoly: gPositiveX is not long enough: %lld >= %llu", (long long)e, (unsigned long long)(dd + 1));
-            return fail(SONIC_ERR_SRS_TOO_SHORT, "openPoly: gNegativeX is not long enough: %lld >= %llu", (long long)(-e - 1), (unsigned long long)dd);
-        }
-
-    // ---- field values in record order (Protocol.hs:28-38, Signature.hs:22-29) ---------------------
-    std::vector<uint8_t> f32((size_t)nF * 32);
-    {
-        uint8_t* o = f32.data();
-        auto putF = [&](const Fr& v) { memcpy(o, v.l, 32); o += 32; };
-        if (has_main) { putF(h_vals[v_a]); putF(h_vals[v_b]); putF(h_vals[v_s]); }   // prA prB prS
-        for (uint32_t j = 0; j < M; ++j) putF(h_vals[v_sj[j]]);                       // s_j
-        for (uint32_t j = 0; j < M; ++j) putF(h_vals[v_spj[j]]);                      // s'_j
-        putF(h_rnd[6 + 2 * M]);                                                       // hscU
-        putF(h_rnd[7 + 2 * M]);                                                       // hscV
-    }
-    if (sharded) {
-        memcpy(out, h_comp.data(), h_comp.size());
-        memcpy(out + h_comp.size(), f32.data(), f32.size());
-    } else {
-        assemble_proof(has_main, M, h_comp.data(), f32.data(), out);
-    }
-    (void)v_t; (void)v_qv; (void)v_wpj;
+    nvtxRangePop();
     return SONIC_OK;
+}
+
+void prove_collect_timing(Ctx& cx) {
+    msm_collect_timing(cx);
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, cx.ev[4], cx.ev[5]) == cudaSuccess) cx.timing_ms["poly"] = ms;
 }
 
 }  // namespace sonic

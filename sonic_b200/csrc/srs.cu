@@ -156,37 +156,92 @@ static int srs_table_bits(uint64_t npoints) {
     return best;
 }
 
-// Generates the resident point array.  d_canon: x, alpha canonical (2 Fr) in device memory.
-// Level 0 is the SRS itself; with pre_c > 0, level j holds the same points times 2^(pre_c j),
-// obtained from the same fixed-base table with the scalar multiplied by 2^(pre_c j) mod r.
-void srs_generate(Ctx& cx, uint64_t d, const Fr* d_canon, G1Affine* d_points, int pre_c, void* d_g2_points) {
+// Generates elements [first, first + count) of every level of the resident point array (flat index
+// family * (2d+1) + k + d); the whole array when first = 0, count = 2*(2d+1).  A multi-GPU runtime
+// gives every device one slice and all-gathers the levels (capi.cu).  d_canon: x, alpha canonical
+// (2 Fr) in device memory.  Level 0 is the SRS itself; with pre_c > 0, level j holds the same points
+// times 2^(pre_c j), obtained from the same fixed-base table with the scalar multiplied by
+// 2^(pre_c j) mod r.  The scalars x^k, alpha x^k are cheap (two Fr products per element against
+// 16 x 3000 LMAC for the point) and are computed in full on every device.
+void srs_generate(Ctx& cx, uint64_t d, const Fr* d_canon, G1Affine* d_points, int pre_c, uint64_t first, uint64_t count,
+                  void* d_g2_points) {
     Arena& ar = cx.arena;
     const uint64_t stride = 2 * d + 1, npts = 2 * stride;
     const int levels = pre_c > 0 ? (255 + pre_c - 1) / pre_c : 1;
+    if (first > npts) first = npts;
+    if (count > npts - first) count = npts - first;
     Fr* mont = ar.get<Fr>(3);
     SONIC_LAUNCH(k_srs_params, 1, 32, 0, d_canon, mont);
     Fr* scal_m = ar.get<Fr>(npts);
     SONIC_LAUNCH(k_srs_scalars, dim3(div_up(d / SRS_RUN + 1, 128), 2), 128, 0, mont, d, scal_m);
-    Fr* consts = ar.get<Fr>(levels);
-    SONIC_LAUNCH(k_level_consts, div_up(levels, 32), 32, 0, pre_c > 0 ? pre_c : 1, levels, consts);
-    const int w = srs_table_bits(npts * (uint64_t)levels);
-    const int Wt = (255 + w - 1) / w;
-    const size_t tsize = (size_t)Wt << w;
-    G1XYZZ* Tx = ar.get<G1XYZZ>(tsize);
-    G1Affine* Ta = ar.get<G1Affine>(tsize);
-    SONIC_LAUNCH(k_tbl_bases, div_up(Wt, 32), 32, 0, Tx, w, Wt);
-    for (int l = 1; l < w; ++l)
-        SONIC_LAUNCH(k_tbl_level, dim3(div_up(1u << l, 128), (unsigned)Wt), 128, 0, Tx, w, Wt, l);
-    SONIC_LAUNCH(k_batch_affine, div_up(div_up(tsize, AFF_BATCH), 128), 128, 0, Tx, Ta, (uint64_t)tsize);
-    Fr* scal = ar.get<Fr>(npts);
-    G1XYZZ* px = ar.get<G1XYZZ>(npts);
-    const uint64_t hole = stride + d;  // alpha family, exponent 0: g^alpha is not part of the SRS
-    for (int j = 0; j < levels; ++j) {
-        SONIC_LAUNCH(k_level_scalars, div_up(npts, 256), 256, 0, scal_m, consts + j, npts, scal);
-        SONIC_LAUNCH(k_fixed_base, div_up(npts, 128), 128, 0, scal, Ta, w, Wt, npts, hole, px);
-        SONIC_LAUNCH(k_batch_affine, div_up(div_up(npts, AFF_BATCH), 128), 128, 0, px, d_points + (size_t)j * npts, npts);
+    if (count) {
+        Fr* consts = ar.get<Fr>(levels);
+        SONIC_LAUNCH(k_level_consts, div_up(levels, 32), 32, 0, pre_c > 0 ? pre_c : 1, levels, consts);
+        const int w = srs_table_bits(count * (uint64_t)levels);
+        const int Wt = (255 + w - 1) / w;
+        const size_t tsize = (size_t)Wt << w;
+        G1XYZZ* Tx = ar.get<G1XYZZ>(tsize);
+        G1Affine* Ta = ar.get<G1Affine>(tsize);
+        SONIC_LAUNCH(k_tbl_bases, div_up(Wt, 32), 32, 0, Tx, w, Wt);
+        for (int l = 1; l < w; ++l)
+            SONIC_LAUNCH(k_tbl_level, dim3(div_up(1u << l, 128), (unsigned)Wt), 128, 0, Tx, w, Wt, l);
+        SONIC_LAUNCH(k_batch_affine, div_up(div_up(tsize, AFF_BATCH), 128), 128, 0, Tx, Ta, (uint64_t)tsize);
+        Fr* scal = ar.get<Fr>(count);
+        G1XYZZ* px = ar.get<G1XYZZ>(count);
+        // alpha family, exponent 0: g^alpha is not part of the SRS
+        const uint64_t hole_abs = stride + d;
+        const uint64_t hole = hole_abs >= first && hole_abs < first + count ? hole_abs - first : ~0ull;
+        for (int j = 0; j < levels; ++j) {
+            SONIC_LAUNCH(k_level_scalars, div_up(count, 256), 256, 0, scal_m + first, consts + j, count, scal);
+            SONIC_LAUNCH(k_fixed_base, div_up(count, 128), 128, 0, scal, Ta, w, Wt, count, hole, px);
+            SONIC_LAUNCH(k_batch_affine, div_up(div_up(count, AFF_BATCH), 128), 128, 0, px, d_points + (size_t)j * npts + first, count);
+        }
     }
     if (d_g2_points) srs_generate_g2(cx, scal_m, npts, d_g2_points);
+}
+
+// ---- window tables restricted to the exponent ranges a circuit size touches -----------------------------
+// `prove` at n gates reads g^{x^k} for k in [-4n-8, 3n] and g^{alpha x^k} for k in [-4n-8, 3n] and
+// [d-3n-4, d] only (the shapes of Protocol.hs:63,73,79-81 and Signature.hs:42-63): 17n points out of
+// 4d+1.  Their multiples 2^(c j) P come from c doublings of the level below -- no trapdoor, so a loaded
+// SRS can have them too -- and cost about what the fixed-base path pays per point (c x 7 products).
+__global__ void __launch_bounds__(128) k_table_level(const G1Affine* __restrict__ prev, uint32_t n, int c, G1XYZZ* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1XYZZ p = g1_mdbl(load_affine(prev + i));
+    for (int k = 1; k < c; ++k) p = g1_dbl(p);
+    store_xyzz(out + i, p);
+}
+
+void tables_build(Ctx& cx, const SrsRep& srs, const TableRange* ranges, int nranges, int c, RestrictedTables* out) {
+    tables_free(out);
+    uint64_t size = 0;
+    for (int i = 0; i < nranges; ++i) {
+        out->range[i] = ranges[i];
+        out->range[i].offset = (uint32_t)size;
+        size += (uint64_t)(ranges[i].hi - ranges[i].lo + 1);
+    }
+    const int W = (255 + c - 1) / c;
+    if (size == 0 || size * (uint64_t)W >= (1ull << 31)) return;
+    SONIC_CUDA(cudaMalloc((void**)&out->points, size * (size_t)W * sizeof(G1Affine)));
+    out->nranges = nranges;
+    out->size = (uint32_t)size;
+    out->tables.c = c;
+    out->tables.W = W;
+    out->tables.stride = (uint32_t)size;
+    for (int i = 0; i < nranges; ++i)
+        SONIC_CUDA(cudaMemcpyAsync(out->points + out->range[i].offset, srs.points + srs.index(ranges[i].family, ranges[i].lo),
+                                   (size_t)(ranges[i].hi - ranges[i].lo + 1) * sizeof(G1Affine), cudaMemcpyDeviceToDevice, cx.stream));
+    G1XYZZ* px = cx.arena.get<G1XYZZ>(size);
+    for (int j = 1; j < W; ++j) {
+        SONIC_LAUNCH(k_table_level, div_up(size, 128), 128, 0, out->points + (size_t)(j - 1) * size, (uint32_t)size, c, px);
+        SONIC_LAUNCH(k_batch_affine, div_up(div_up(size, AFF_BATCH), 128), 128, 0, px, out->points + (size_t)j * size, size);
+    }
+}
+
+void tables_free(RestrictedTables* t) {
+    if (t->points) cudaFree(t->points);
+    *t = RestrictedTables();
 }
 
 }  // namespace sonic
