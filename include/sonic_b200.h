@@ -204,7 +204,8 @@ int sonic_prove_combine_device(uint64_t Q, uint32_t world, const void* d_gathere
                                uint8_t* proof_out, uint64_t cap, uint64_t* written);
 
 /* Same proof, with the assignment (aL | aR | aO, 3n Fr, canonical) and the draws already
- * resident in device memory; `rnd_host` is the host copy of the draws (zero checks, hscU/hscV).
+ * resident in device memory (of devices[0]; the other devices of a multi-GPU runtime pull them over
+ * NVLink); `rnd_host` is the host copy of the draws (zero checks, hscU/hscV).
  * Used by bench.py to time the path without the host->device copy of the inputs. */
 int sonic_prove_device(const sonic_srs* srs, const sonic_circuit* circuit, const void* d_assignment,
                        const void* d_rnd, const uint8_t* rnd_host, uint8_t* proof_out, uint64_t cap,
@@ -220,6 +221,15 @@ int sonic_prove_shard_device(const sonic_srs* srs, const sonic_circuit* circuit,
 int sonic_hsc_prove(const sonic_srs* srs, const sonic_circuit* circuit, uint64_t m,
                     const uint8_t* yzs, const uint8_t* uv, uint8_t* out, uint64_t cap,
                     uint64_t* written);
+
+/* The same hscProve for ANY sparse `BiVLaurent Fr`, as the reference's signature allows and its test
+ * builds it (`sPoly weights`, test/Test/Signature.hs:30-36): s(X,Y) = sum_t coeff_t X^(eX[t]) Y^(eY[t]),
+ * nterms terms in any order (outer variable X, inner Y: src/Sonic/Utils.hs:15); terms with a zero
+ * coefficient are ignored and repeated monomials add up, as in the sparse normal form.  |exponent| <= 2^26.
+ * A shim walks `GHC.Exts.toList sXY` (and `toList` of each inner polynomial) to produce the three arrays. */
+int sonic_hsc_prove_terms(const sonic_srs* srs, uint64_t nterms, const int64_t* eX, const int64_t* eY,
+                          const uint8_t* coeff32, uint64_t m, const uint8_t* yzs, const uint8_t* uv,
+                          uint8_t* out, uint64_t cap, uint64_t* written);
 
 /* Verifier-side G1 folding (the pairings stay on the host library).
  * pcV (src/Sonic/CommitmentScheme.hs:51-68) for k checks (F_i, z_i, (v_i, W_i)) with caller-chosen

@@ -17,6 +17,7 @@ from .api import (  # noqa: F401
     SRS,
     commitPoly,
     hscProve,
+    hscProveBiV,
     msm,
     msm_partial,
     g1_sum,

@@ -76,7 +76,6 @@ class _Circuit:
     """Weights resident on the device across proofs (sonic_circuit_load)."""
 
     def __init__(self, c: ArithCircuit):
-        capi.init()
         w = c.weights
         if not w.wL or not w.wL[0]:
             raise SonicError(1, "Empty weights")
@@ -91,6 +90,7 @@ class _Circuit:
                     raise SonicError(1, f"{name}[{q}] has {len(row)} entries, expected n = {self.n}")
         if len(c.cs) != self.Q:
             raise SonicError(1, f"cs has {len(c.cs)} entries, expected Q = {self.Q}")
+        capi.init()
         h = c_void_p()
         if c.sparse:
             import numpy as np
@@ -370,6 +370,29 @@ def hscProve(srs: SRS, circuit: ArithCircuit, yzs: Sequence[Tuple[int, int]], u:
     written = c_uint64(0)
     flat = _frs([x for pair in yzs for x in pair])
     check(lib().sonic_hsc_prove(srs._h, ch.h, m, flat, _frs([u, v]), out, size, ctypes.byref(written)))
+    return _parse_hsc(out.raw, m)
+
+
+def hscProveBiV(srs: SRS, sXY: Dict[int, Dict[int, int]], yzs: Sequence[Tuple[int, int]], u: int, v: int) -> HscProof:
+    """`hscProve srs sXY yzs` for ANY sparse `BiVLaurent Fr` (src/Sonic/Signature.hs:32-37; outer variable
+    X, inner Y: {eX: {eY: coeff}}), through sonic_hsc_prove_terms -- what the reference's own test calls
+    with `sPoly weights` (test/Test/Signature.hs:30-36)."""
+    import numpy as np
+
+    capi.init()
+    terms = [(ex, ey, c % R_MODULUS) for ex, inner in sXY.items() for ey, c in inner.items()]
+    m = len(yzs)
+    if any(len(p) != 2 for p in yzs):
+        raise SonicError(1, "yzs holds (y_j, z_j) pairs")
+    eX = np.array([t[0] for t in terms], dtype=np.int64)
+    eY = np.array([t[1] for t in terms], dtype=np.int64)
+    coeff = _frs([t[2] for t in terms])
+    size = (4 * m + 2) * 48 + (2 * m + 2) * 32
+    out = ctypes.create_string_buffer(size)
+    written = c_uint64(0)
+    flat = _frs([x for pair in yzs for x in pair])
+    check(lib().sonic_hsc_prove_terms(srs._h, len(terms), eX.ctypes.data if terms else None, eY.ctypes.data if terms else None,
+                                      coeff if terms else None, m, flat, _frs([u, v]), out, size, ctypes.byref(written)))
     return _parse_hsc(out.raw, m)
 
 

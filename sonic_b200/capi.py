@@ -68,6 +68,7 @@ SYMBOLS = {
     "sonic_prove_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, _u8p, _u8p, c_uint64, POINTER(c_uint64)]),
     "sonic_prove_shard_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, _u8p, ctypes.c_uint32, ctypes.c_uint32, _u8p, c_uint64, POINTER(c_uint64)]),
     "sonic_hsc_prove": (c_int, [c_void_p, c_void_p, c_uint64, _u8p, _u8p, _u8p, c_uint64, POINTER(c_uint64)]),
+    "sonic_hsc_prove_terms": (c_int, [c_void_p, c_uint64, c_void_p, c_void_p, _u8p, c_uint64, _u8p, _u8p, _u8p, c_uint64, POINTER(c_uint64)]),
     "sonic_pcv_fold": (c_int, [c_uint64, _u8p, _u8p, _u8p, _u8p, _u8p, c_void_p, ctypes.c_uint32, _u8p]),
     "sonic_set_option": (c_int, [c_char_p, c_int64]),
     "sonic_last_timing_ms": (c_double, [c_char_p]),
@@ -91,6 +92,8 @@ def _preload_nccl() -> None:
     and the loader keeps whichever came first.  Load the bundled one first when it is installed, so that
     the order of `import torch` / `import sonic_b200` does not matter; a process without torch gets the
     system library through the normal search path."""
+    if os.environ.get("SONIC_NO_NCCL_PRELOAD"):
+        return
     try:
         import importlib.util
 
@@ -144,6 +147,9 @@ def init(device=None) -> None:
     dev = (c_int * len(devices))(*devices)
     check(lib().sonic_init(dev, len(devices)))
     _ready = True
+    import atexit
+
+    atexit.register(shutdown)   # NCCL communicators and worker threads are torn down before the interpreter goes
 
 
 def device_count() -> int:

@@ -613,6 +613,19 @@ int sonic_init(const int* devices, int ndev) {
         R.vote.n = ndev;
         R.ready = true;
         if (ndev > 1) {
+            // peer access over NVLink between every pair: device-resident inputs of one device are read by the others directly
+            for (int r = 0; r < ndev; ++r) {
+                SONIC_CUDA(cudaSetDevice(devs[r]));
+                for (int q = 0; q < ndev; ++q) {
+                    if (q == r) continue;
+                    int can = 0;
+                    if (cudaDeviceCanAccessPeer(&can, devs[r], devs[q]) == cudaSuccess && can) {
+                        cudaError_t pe = cudaDeviceEnablePeerAccess(devs[q], 0);
+                        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) throw CudaError{pe, "cudaDeviceEnablePeerAccess", __LINE__};
+                        cudaGetLastError();
+                    }
+                }
+            }
             // one communicator per device, all in this process; every collective below is issued by the
             // device's own thread on the device's own stream
             ncclResult_t nr = ncclCommInitAll(R.comm, ndev, devs);
@@ -630,6 +643,13 @@ int sonic_init(const int* devices, int ndev) {
         }
         SONIC_CUDA(cudaSetDevice(devs[0]));
         ctx_bind(&ctx_slots()[0]);
+        // a process that exits without sonic_shutdown must not hang in the teardown of live NCCL communicators and
+        // worker threads: registered after the CUDA runtime came up, so it runs before the runtime's own exit handler
+        static bool at_exit_registered = false;
+        if (!at_exit_registered) {
+            at_exit_registered = true;
+            atexit([] { sonic_shutdown(); });
+        }
     } catch (const CudaError& e) {
         cudaGetLastError();
         shutdown_locked();
@@ -1229,7 +1249,8 @@ int prove_single(Ctx& cx, SrsRep& srs, const CircuitRep& circ, uint64_t n, uint6
 // the exchange records, fold on device 0.  `assignment`: aL | aR | aO contiguous on the host, or three
 // separate host pointers.
 int prove_all_devices(const sonic_srs* srs, const sonic_circuit* circuit, const uint8_t* aL, const uint8_t* aR,
-                      const uint8_t* aO, const uint8_t* rnd, uint8_t* proof_out, uint64_t cap, uint64_t* written) {
+                      const uint8_t* aO, const void* d_assignment, const void* d_rnd_dev, const uint8_t* rnd, uint8_t* proof_out,
+                      uint64_t cap, uint64_t* written) {
     Runtime& R = rt();
     const uint64_t n = circuit->n, Q = circuit->Q;
     const ProveLayout lay((uint32_t)Q, true);
@@ -1238,11 +1259,29 @@ int prove_all_devices(const sonic_srs* srs, const sonic_circuit* circuit, const 
         uint8_t* d_all = cx.arena.get<uint8_t>(lay.rec_bytes() * (size_t)R.ndev);
         int rc = attempt(cx, [&]() -> int {
             Timer tm(cx);
-            Fr* d_in = cx.arena.get<Fr>(3 * n);
-            SONIC_CUDA(cudaMemcpyAsync(d_in, aL, n * 32, cudaMemcpyHostToDevice, cx.stream));
-            SONIC_CUDA(cudaMemcpyAsync(d_in + n, aR, n * 32, cudaMemcpyHostToDevice, cx.stream));
-            SONIC_CUDA(cudaMemcpyAsync(d_in + 2 * n, aO, n * 32, cudaMemcpyHostToDevice, cx.stream));
-            const Fr* d_rnd = upload_fr(cx, rnd, 2 * Q + 8);
+            const Fr* d_in;
+            const Fr* d_rnd;
+            if (d_assignment) {
+                // inputs resident in the memory of device 0: the other devices pull them over NVLink (peer copy)
+                if (r == 0) {
+                    d_in = (const Fr*)d_assignment;
+                    d_rnd = (const Fr*)d_rnd_dev;
+                } else {
+                    Fr* in = cx.arena.get<Fr>(3 * n);
+                    Fr* rn = cx.arena.get<Fr>(2 * Q + 8);
+                    SONIC_CUDA(cudaMemcpyPeerAsync(in, cx.device, d_assignment, ctx_slots()[0].device, 3 * n * 32, cx.stream));
+                    SONIC_CUDA(cudaMemcpyPeerAsync(rn, cx.device, d_rnd_dev, ctx_slots()[0].device, (2 * Q + 8) * 32, cx.stream));
+                    d_in = in;
+                    d_rnd = rn;
+                }
+            } else {
+                Fr* in = cx.arena.get<Fr>(3 * n);
+                SONIC_CUDA(cudaMemcpyAsync(in, aL, n * 32, cudaMemcpyHostToDevice, cx.stream));
+                SONIC_CUDA(cudaMemcpyAsync(in + n, aR, n * 32, cudaMemcpyHostToDevice, cx.stream));
+                SONIC_CUDA(cudaMemcpyAsync(in + 2 * n, aO, n * 32, cudaMemcpyHostToDevice, cx.stream));
+                d_in = in;
+                d_rnd = upload_fr(cx, rnd, 2 * Q + 8);
+            }
             ensure_tables(cx, *srs->rep[r], n, Q, true);
             return prove_enqueue(cx, *srs->rep[r], *circuit->rep[r], d_in, d_rnd, (uint32_t)Q, true, (uint32_t)r, (uint32_t)R.ndev, d_rec);
         });
@@ -1285,7 +1324,7 @@ int sonic_prove(const sonic_srs* srs, const sonic_circuit* circuit, const uint8_
     uint64_t n, Q;
     int rc = prove_precheck(srs, circuit, rnd, &n, &Q);
     if (rc) return rc;
-    if (rt().ready && rt().ndev > 1) return prove_all_devices(srs, circuit, aL, aR, aO, rnd, proof_out, cap, written);
+    if (rt().ready && rt().ndev > 1) return prove_all_devices(srs, circuit, aL, aR, aO, nullptr, nullptr, rnd, proof_out, cap, written);
     return guarded([&](Ctx& cx) {
         Fr* d_in = cx.arena.get<Fr>(3 * n);
         SONIC_CUDA(cudaMemcpyAsync(d_in, aL, n * 32, cudaMemcpyHostToDevice, cx.stream));
@@ -1431,6 +1470,7 @@ int sonic_prove_device(const sonic_srs* srs, const sonic_circuit* circuit, const
     uint64_t n, Q;
     int rc = prove_precheck(srs, circuit, rnd_host, &n, &Q);
     if (rc) return rc;
+    if (rt().ready && rt().ndev > 1) return prove_all_devices(srs, circuit, nullptr, nullptr, nullptr, d_assignment, d_rnd, rnd_host, proof_out, cap, written);
     return guarded([&](Ctx& cx) {
         return prove_single(cx, *srs->rep[0], *circuit->rep[0], n, Q, (uint32_t)Q, true, d_assignment, true, d_rnd, rnd_host, proof_out, cap, written);
     });
@@ -1451,6 +1491,47 @@ int sonic_hsc_prove(const sonic_srs* srs, const sonic_circuit* circuit, uint64_t
         if (fr_bytes_zero(&rnd[32 * i])) return fail(SONIC_ERR_DIV_BY_ZERO, "hscProve: recip 0 (an evaluation point is zero)");
     return guarded([&](Ctx& cx) {
         return prove_single(cx, *srs->rep[0], *circuit->rep[0], circuit->n, circuit->Q, (uint32_t)m, false, nullptr, true, nullptr, rnd.data(), out, cap, written);
+    });
+}
+
+int sonic_hsc_prove_terms(const sonic_srs* srs, uint64_t nterms, const int64_t* eX, const int64_t* eY, const uint8_t* coeff32,
+                          uint64_t m, const uint8_t* yzs, const uint8_t* uv, uint8_t* out, uint64_t cap, uint64_t* written) {
+    if (!srs || (nterms && (!eX || !eY || !coeff32)) || (!yzs && m) || !uv || !out) return fail(SONIC_ERR_INVALID_ARG, "null argument");
+    if (m >= (1u << 12) || nterms >= (1ull << 28)) return fail(SONIC_ERR_INVALID_ARG, "too many (y, z) pairs or terms");
+    std::vector<uint8_t> rnd((2 * m + 8) * 32, 0);
+    for (uint64_t j = 0; j < m; ++j) {
+        memcpy(&rnd[(6 + j) * 32], yzs + 64 * j, 32);
+        memcpy(&rnd[(6 + m + j) * 32], yzs + 64 * j + 32, 32);
+    }
+    memcpy(&rnd[(6 + 2 * m) * 32], uv, 64);
+    // a zero evaluation point only matters where a negative power is taken (`eval` / `pow` with recip): keep
+    // the reference's behaviour by refusing it exactly then
+    bool neg_x = false, neg_y = false;
+    for (uint64_t t = 0; t < nterms; ++t) {
+        if (fr_bytes_zero(coeff32 + 32 * t)) continue;
+        neg_x = neg_x || eX[t] < 0;
+        neg_y = neg_y || eY[t] < 0;
+    }
+    for (uint64_t j = 0; j < m; ++j) {
+        if (neg_y && fr_bytes_zero(&rnd[(6 + j) * 32])) return fail(SONIC_ERR_DIV_BY_ZERO, "hscProve: recip 0 (y_%" PRIu64 " = 0 with negative powers of Y)", j + 1);
+        if (neg_x && fr_bytes_zero(&rnd[(6 + m + j) * 32])) return fail(SONIC_ERR_DIV_BY_ZERO, "hscProve: recip 0 (z_%" PRIu64 " = 0 with negative powers of X)", j + 1);
+    }
+    if ((neg_x && fr_bytes_zero(&rnd[(6 + 2 * m) * 32])) || (neg_y && fr_bytes_zero(&rnd[(7 + 2 * m) * 32])))
+        return fail(SONIC_ERR_DIV_BY_ZERO, "hscProve: recip 0 (u or v is zero with negative powers)");
+    for (uint64_t i = 6; i < 2 * m + 8; ++i)
+        if (fr_bytes_zero(&rnd[32 * i])) return fail(SONIC_ERR_INVALID_ARG, "hscProve: a zero evaluation point is not supported by this entry");
+    return guarded([&](Ctx& cx) {
+        const ProveLayout lay((uint32_t)m, false);
+        Timer tm(cx);
+        const Fr* d_rnd = upload_fr(cx, rnd.data(), 2 * m + 8);
+        uint8_t* d_out = cx.arena.get<uint8_t>(lay.out_bytes());
+        int rc = hsc_terms_enqueue(cx, *srs->rep[0], nterms, eX, eY, coeff32, (uint32_t)m, d_rnd, d_out);
+        if (rc) return rc;
+        uint8_t* h = pinned(cx, lay.out_bytes());
+        SONIC_CUDA(cudaMemcpyAsync(h, d_out, lay.out_bytes(), cudaMemcpyDeviceToHost, cx.stream));
+        tm.stop();
+        msm_collect_timing(cx);
+        return prove_finish(lay, h, rnd.data(), out, cap, written);
     });
 }
 

@@ -181,6 +181,9 @@ void prove_fold_enqueue(Ctx& cx, const ProveLayout& lay, uint32_t world, const u
 int prove_finish(const ProveLayout& lay, const uint8_t* h_out, const uint8_t* rnd_host, uint8_t* proof, uint64_t cap,
                  uint64_t* written);
 void prove_collect_timing(Ctx& cx);
+// hscProve for a sparse s(X,Y) given as terms c_t X^(eX_t) Y^(eY_t) (host arrays); result buffer of ProveLayout(M, false)
+int hsc_terms_enqueue(Ctx& cx, SrsRep& srs, uint64_t nterms, const int64_t* eX, const int64_t* eY, const uint8_t* coeff32,
+                      uint32_t M, const Fr* d_rnd, uint8_t* d_result);
 }  // namespace sonic
 
 // ---- the public handles: one replica per device of the sonic_init list -----------------------

@@ -531,6 +531,96 @@ __global__ void __launch_bounds__(256) k_first_violation(const Fr* __restrict__ 
     if (!s[i].is_zero()) atomicMin(out, (uint32_t)(lo + (int64_t)i + (int64_t)(1u << 30)));
 }
 
+// The G1 half of a proof: range scans and the batched MSM over this rank's part [piece_lo, piece_hi) of every
+// window.  world == 1 (`sharded` false): compressed results straight into the result buffer; else raw
+// partial sums into the exchange record (the identity for MSMs this rank holds no part of).
+static int enqueue_msms(Ctx& cx, SrsRep& srs, const std::vector<ProofMsm>& pm, const std::vector<int64_t>& piece_lo,
+                        const std::vector<int64_t>& piece_hi, uint32_t* viol, bool sharded, uint8_t* d_result) {
+    Arena& ar = cx.arena;
+    cudaStream_t st = cx.stream;
+    const int64_t d = (int64_t)srs.d;
+    const uint32_t nm = (uint32_t)pm.size();
+    // range / hole checks: first non-zero scalar outside what the SRS holds, per MSM, by the ranks that
+    // built the vector (the fold takes the minimum, so every rank reaches the same verdict)
+    std::vector<MsmJob> jobs(nm);
+    std::vector<int64_t> slice_lo(nm, 0);
+    for (uint32_t i = 0; i < nm; ++i) {
+        const ProofMsm& m = pm[i];
+        const int64_t lo = m.lo, hi = m.lo + (int64_t)m.len;
+        struct Rng { int64_t a, b; } r[3] = {{0, 0}, {0, 0}, {0, 0}};
+        if (lo < -d) r[0] = {lo, std::min(hi, -d)};
+        if (m.family == SONIC_FAMILY_ALPHA && lo <= 0 && 0 < hi) r[1] = {0, 1};
+        if (hi > d + 1) r[2] = {std::max(lo, d + 1), hi};
+        for (int k = 0; k < 3; ++k) {
+            if (r[k].b > r[k].a && m.scal) {
+                const uint32_t a = (uint32_t)(r[k].a - lo), b = (uint32_t)(r[k].b - lo);
+                SONIC_LAUNCH(k_first_violation, div_up(b - a, 256), 256, 0, m.scal, a, b, lo, viol + 3 * (size_t)i + k);
+            }
+        }
+        // the part of this window inside the rank's run of terms (the whole clipped window when not sharded)
+        const int64_t clo = piece_lo[i], chi = piece_hi[i];
+        slice_lo[i] = clo;
+        jobs[i].point_base = 0;
+        jobs[i].n = (uint32_t)(chi - clo);
+        jobs[i].scalar_off = 0;
+        jobs[i].pad = 0;
+    }
+    // ---- bases: the full-range window tables, else tables restricted to this circuit size, else none ----
+    const G1Affine* d_points = srs.points;
+    MsmTables tables = srs.tables;
+    bool restricted = false;
+    if (srs.tables.c == 0 && srs.rt.points) {
+        restricted = true;
+        for (uint32_t i = 0; i < nm && restricted; ++i)
+            if (jobs[i].n && srs.rt.find(pm[i].family, slice_lo[i], jobs[i].n) < 0) restricted = false;
+        if (restricted) { d_points = srs.rt.points; tables = srs.rt.tables; }
+    }
+    for (uint32_t i = 0; i < nm; ++i) {
+        if (!jobs[i].n) continue;
+        jobs[i].point_base = restricted ? (uint32_t)srs.rt.find(pm[i].family, slice_lo[i], jobs[i].n) : (uint32_t)srs.index(pm[i].family, slice_lo[i]);
+    }
+    // all scalar vectors live in the arena; express them as offsets from the lowest address
+    const Fr* sbase = nullptr;
+    for (uint32_t i = 0; i < nm; ++i) {
+        if (jobs[i].n == 0) continue;
+        if (!pm[i].scal) return fail(SONIC_ERR_INVALID_ARG, "internal: MSM %u has terms on this rank but no scalars", i);
+        if (!sbase || pm[i].scal < sbase) sbase = pm[i].scal;
+    }
+    for (uint32_t i = 0; i < nm; ++i)
+        if (jobs[i].n) jobs[i].scalar_off = (uint32_t)((pm[i].scal - sbase) + (slice_lo[i] - pm[i].lo));
+    nvtxRangePushA("sonic.prove.msm");
+    if (sharded) {
+        // only this rank's MSMs (whole or partial) enter the pipeline; the others contribute the identity (zeros)
+        G1Affine* d_aff = ar.get<G1Affine>(nm);
+        SONIC_CUDA(cudaMemsetAsync(d_aff, 0, (size_t)nm * sizeof(G1Affine), st));
+        std::vector<uint32_t> own;
+        for (uint32_t i = 0; i < nm; ++i) if (jobs[i].n > 0) own.push_back(i);
+        G1Affine* d_mine = ar.get<G1Affine>(own.size() ? own.size() : 1);
+        for (size_t first = 0; first < own.size(); first += MSM_MAX_JOBS) {
+            const size_t cnt = std::min<size_t>(MSM_MAX_JOBS, own.size() - first);
+            std::vector<MsmJob> part;
+            for (size_t k = 0; k < cnt; ++k) part.push_back(jobs[own[first + k]]);
+            msm_run(cx, d_points, tables, (const uint32_t*)sbase, part, d_mine + first, nullptr);
+        }
+        // runs of consecutive record indices move in one copy
+        for (size_t k = 0; k < own.size();) {
+            size_t e = k + 1;
+            while (e < own.size() && own[e] == own[e - 1] + 1) ++e;
+            SONIC_CUDA(cudaMemcpyAsync(d_aff + own[k], d_mine + k, (e - k) * sizeof(G1Affine), cudaMemcpyDeviceToDevice, st));
+            k = e;
+        }
+        SONIC_LAUNCH(k_points_to_raw, div_up(nm, 64), 64, 0, d_aff, nm, reinterpret_cast<Fq*>(d_result));
+    } else {
+        for (uint32_t first = 0; first < nm; first += MSM_MAX_JOBS) {
+            const uint32_t cnt = std::min<uint32_t>(MSM_MAX_JOBS, nm - first);
+            std::vector<MsmJob> part(jobs.begin() + first, jobs.begin() + first + cnt);
+            msm_run(cx, d_points, tables, (const uint32_t*)sbase, part, nullptr, d_result + (size_t)first * 48);
+        }
+    }
+    nvtxRangePop();
+    return SONIC_OK;
+}
+
 int prove_enqueue(Ctx& cx, SrsRep& srs, const CircuitRep& circ_, const Fr* d_in, const Fr* d_rnd, uint32_t M, bool has_main,
                   uint32_t rank, uint32_t world, uint8_t* d_result) {
     const CircuitRep* circ = &circ_;
@@ -775,7 +865,7 @@ int prove_enqueue(Ctx& cx, SrsRep& srs, const CircuitRep& circ_, const Fr* d_in,
     suy.lo = -(int64_t)n;
     if (need_suy) {
         suy.mont = ar.get<Fr>(suy.len);
-        suy.canon = ar.get<Fr>(suy.len);
+        suy.canon = mine(iC) ? ar.get<Fr>(suy.len) : nullptr;   // committed to (and range-scanned) only where C is summed
         SONIC_LAUNCH(k_build_suy_pm, div_up(2 * n + 1, 256), 256, 0, fwd(PT_U), n, Q, suy.mont);
         Fr* part = ar.get<Fr>((size_t)Q * SUY_PARTS);
         if (circ->sparse) {
@@ -896,85 +986,185 @@ int prove_enqueue(Ctx& cx, SrsRep& srs, const CircuitRep& circ_, const Fr* d_in,
     for (uint32_t i = 0; i < nm; ++i)
         if (pm[i].lo != shape[i].lo || pm[i].len != shape[i].len) return fail(SONIC_ERR_INVALID_ARG, "internal: MSM %u does not match its shape", i);
 
-    // range / hole checks: first non-zero scalar outside what the SRS holds, per MSM, by the ranks that
-    // built the vector (the fold takes the minimum, so every rank reaches the same verdict)
-    std::vector<MsmJob> jobs(nm);
-    std::vector<int64_t> slice_lo(nm, 0);
-    for (uint32_t i = 0; i < nm; ++i) {
-        const ProofMsm& m = pm[i];
-        const int64_t lo = m.lo, hi = m.lo + (int64_t)m.len;
-        struct Rng { int64_t a, b; } r[3] = {{0, 0}, {0, 0}, {0, 0}};
-        if (lo < -d) r[0] = {lo, std::min(hi, -d)};
-        if (m.family == SONIC_FAMILY_ALPHA && lo <= 0 && 0 < hi) r[1] = {0, 1};
-        if (hi > d + 1) r[2] = {std::max(lo, d + 1), hi};
-        for (int k = 0; k < 3; ++k) {
-            if (r[k].b > r[k].a && m.scal) {
-                const uint32_t a = (uint32_t)(r[k].a - lo), b = (uint32_t)(r[k].b - lo);
-                SONIC_LAUNCH(k_first_violation, div_up(b - a, 256), 256, 0, m.scal, a, b, lo, viol + 3 * (size_t)i + k);
-            }
-        }
-        // the part of this window inside the rank's run of terms (the whole clipped window when not sharded)
-        const int64_t clo = piece_lo[i], chi = piece_hi[i];
-        slice_lo[i] = clo;
-        jobs[i].point_base = 0;
-        jobs[i].n = (uint32_t)(chi - clo);
-        jobs[i].scalar_off = 0;
-        jobs[i].pad = 0;
+    return enqueue_msms(cx, srs, pm, piece_lo, piece_hi, viol, sharded, d_result);
+}
+
+// ---- hscProve on a general sparse s(X,Y) (src/Sonic/Signature.hs:32-72) ----------------------------------------
+// The reference's hscProve takes any `BiVLaurent Fr`; its test feeds `sPoly weights`
+// (test/Test/Signature.hs:30-36).  Here s(X,Y) = sum_t c_t X^(a_t) Y^(b_t) arrives as a term list and the
+// two univariate families are evaluated from it directly:
+//   s(X, y_j)[a] = sum over the terms with a_t = a of c_t y_j^(b_t)        (evalY, Utils.hs:20-21)
+//   s(u, Y)[b]   = sum over the terms with b_t = b of c_t u^(a_t)          (evalX, Utils.hs:17-18)
+// (terms sorted by the surviving exponent on the host; one thread per coefficient of the result).
+struct TermRows {
+    const uint32_t* ptr;   // rows + 1
+    const int32_t* exp;    // exponent of the variable being evaluated, per term
+    const Fr* val;         // coefficient, Montgomery
+};
+
+__global__ void __launch_bounds__(128) k_eval_term_rows(TermRows rows, uint32_t nrows, const Fr* __restrict__ tabs, uint64_t tl,
+                                                        const uint32_t* __restrict__ fwd_idx, const uint32_t* __restrict__ inv_idx,
+                                                        Fr* __restrict__ out, uint32_t out_stride) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    const uint32_t b = blockIdx.y;
+    const Fr* pf = tabs + (size_t)fwd_idx[b] * tl;
+    const Fr* pi = tabs + (size_t)inv_idx[b] * tl;
+    Fr acc = Fr::zero();
+    for (uint32_t k = rows.ptr[row]; k < rows.ptr[row + 1]; ++k) {
+        const int32_t e = rows.exp[k];
+        acc = fp_add(acc, fp_mul(rows.val[k], e >= 0 ? pf[e] : pi[-e]));
     }
-    // ---- bases: the full-range window tables, else tables restricted to this circuit size, else none ----
-    const G1Affine* d_points = srs.points;
-    MsmTables tables = srs.tables;
-    bool restricted = false;
-    if (srs.tables.c == 0 && srs.rt.points) {
-        restricted = true;
-        for (uint32_t i = 0; i < nm && restricted; ++i)
-            if (jobs[i].n && srs.rt.find(pm[i].family, slice_lo[i], jobs[i].n) < 0) restricted = false;
-        if (restricted) { d_points = srs.rt.points; tables = srs.rt.tables; }
+    out[(size_t)b * out_stride + row] = acc;
+}
+
+int hsc_terms_enqueue(Ctx& cx, SrsRep& srs, uint64_t nterms, const int64_t* eX, const int64_t* eY, const uint8_t* coeff32,
+                      uint32_t M, const Fr* d_rnd, uint8_t* d_result) {
+    const ProveLayout lay(M, false);
+    const int64_t d = (int64_t)srs.d;
+    Arena& ar = cx.arena;
+    cudaStream_t st = cx.stream;
+    const uint32_t nm = lay.nm;
+    Fr* d_vals = reinterpret_cast<Fr*>(d_result + lay.out_vals());
+    uint32_t* viol = reinterpret_cast<uint32_t*>(d_result + lay.out_status());
+    uint32_t* bad = viol + 3 * (size_t)nm;
+    SONIC_CUDA(cudaMemsetAsync(d_result, 0, lay.out_bytes(), st));
+    SONIC_CUDA(cudaMemsetAsync(viol, 0xff, 12 * (size_t)nm, st));
+    {
+        const uint32_t dw[2] = {(uint32_t)srs.d, (uint32_t)(srs.d >> 32)};
+        SONIC_CUDA(cudaMemcpyAsync(bad + 1, dw, 8, cudaMemcpyHostToDevice, st));
     }
-    for (uint32_t i = 0; i < nm; ++i) {
-        if (!jobs[i].n) continue;
-        jobs[i].point_base = restricted ? (uint32_t)srs.rt.find(pm[i].family, slice_lo[i], jobs[i].n) : (uint32_t)srs.index(pm[i].family, slice_lo[i]);
+    // ---- the term list: zero coefficients are not terms (the sparse normal form drops them) ----------------
+    std::vector<uint32_t> live;
+    int64_t xlo = 0, xhi = 0, ylo = 0, yhi = 0;   // both windows contain exponent 0 (openPoly subtracts f(z) there)
+    const int64_t lim = int64_t(1) << 26;
+    for (uint64_t t = 0; t < nterms; ++t) {
+        const uint64_t* w = reinterpret_cast<const uint64_t*>(coeff32 + 32 * t);
+        uint64_t c[4];
+        memcpy(c, w, 32);
+        if ((c[0] | c[1] | c[2] | c[3]) == 0) continue;
+        if (eX[t] < -lim || eX[t] > lim || eY[t] < -lim || eY[t] > lim) return fail(SONIC_ERR_INVALID_ARG, "term %llu: exponent out of range (|e| <= 2^26)", (unsigned long long)t);
+        live.push_back((uint32_t)t);
+        xlo = std::min(xlo, eX[t]); xhi = std::max(xhi, eX[t]);
+        ylo = std::min(ylo, eY[t]); yhi = std::max(yhi, eY[t]);
     }
-    // all scalar vectors live in the arena; express them as offsets from the lowest address
-    const Fr* sbase = nullptr;
-    for (uint32_t i = 0; i < nm; ++i) {
-        if (jobs[i].n == 0) continue;
-        if (!pm[i].scal) return fail(SONIC_ERR_INVALID_ARG, "internal: MSM %u has terms on this rank but no scalars", i);
-        if (!sbase || pm[i].scal < sbase) sbase = pm[i].scal;
+    const uint32_t nl = (uint32_t)live.size();
+    const uint32_t xlen = (uint32_t)(xhi - xlo + 1), ylen = (uint32_t)(yhi - ylo + 1);
+    // rows by X (the exponent that survives evalY) and by Y (survives evalX); duplicates of a monomial add up
+    std::vector<uint32_t> ptrX(xlen + 1, 0), ptrY(ylen + 1, 0), ordX(nl), ordY(nl);
+    for (uint32_t k = 0; k < nl; ++k) { ptrX[eX[live[k]] - xlo + 1]++; ptrY[eY[live[k]] - ylo + 1]++; }
+    for (uint32_t i = 0; i < xlen; ++i) ptrX[i + 1] += ptrX[i];
+    for (uint32_t i = 0; i < ylen; ++i) ptrY[i + 1] += ptrY[i];
+    {
+        std::vector<uint32_t> cx_(ptrX.begin(), ptrX.end() - 1), cy_(ptrY.begin(), ptrY.end() - 1);
+        for (uint32_t k = 0; k < nl; ++k) { ordX[cx_[eX[live[k]] - xlo]++] = live[k]; ordY[cy_[eY[live[k]] - ylo]++] = live[k]; }
     }
-    for (uint32_t i = 0; i < nm; ++i)
-        if (jobs[i].n) jobs[i].scalar_off = (uint32_t)((pm[i].scal - sbase) + (slice_lo[i] - pm[i].lo));
-    nvtxRangePushA("sonic.prove.msm");
-    if (sharded) {
-        // only this rank's MSMs (whole or partial) enter the pipeline; the others contribute the identity (zeros)
-        G1Affine* d_aff = ar.get<G1Affine>(nm);
-        SONIC_CUDA(cudaMemsetAsync(d_aff, 0, (size_t)nm * sizeof(G1Affine), st));
-        std::vector<uint32_t> own;
-        for (uint32_t i = 0; i < nm; ++i) if (jobs[i].n > 0) own.push_back(i);
-        G1Affine* d_mine = ar.get<G1Affine>(own.size() ? own.size() : 1);
-        for (size_t first = 0; first < own.size(); first += MSM_MAX_JOBS) {
-            const size_t cnt = std::min<size_t>(MSM_MAX_JOBS, own.size() - first);
-            std::vector<MsmJob> part;
-            for (size_t k = 0; k < cnt; ++k) part.push_back(jobs[own[first + k]]);
-            msm_run(cx, d_points, tables, (const uint32_t*)sbase, part, d_mine + first, nullptr);
-        }
-        // runs of consecutive record indices move in one copy
-        for (size_t k = 0; k < own.size();) {
-            size_t e = k + 1;
-            while (e < own.size() && own[e] == own[e - 1] + 1) ++e;
-            SONIC_CUDA(cudaMemcpyAsync(d_aff + own[k], d_mine + k, (e - k) * sizeof(G1Affine), cudaMemcpyDeviceToDevice, st));
-            k = e;
-        }
-        SONIC_LAUNCH(k_points_to_raw, div_up(nm, 64), 64, 0, d_aff, nm, reinterpret_cast<Fq*>(d_result));
-    } else {
-        for (uint32_t first = 0; first < nm; first += MSM_MAX_JOBS) {
-            const uint32_t cnt = std::min<uint32_t>(MSM_MAX_JOBS, nm - first);
-            std::vector<MsmJob> part(jobs.begin() + first, jobs.begin() + first + cnt);
-            msm_run(cx, d_points, tables, (const uint32_t*)sbase, part, nullptr, d_result + (size_t)first * 48);
-        }
+    std::vector<int32_t> expX(nl ? nl : 1), expY(nl ? nl : 1);   // X-rows carry Y exponents and vice versa
+    std::vector<uint8_t> coef(2 * (size_t)(nl ? nl : 1) * 32);
+    for (uint32_t k = 0; k < nl; ++k) {
+        expX[k] = (int32_t)eY[ordX[k]];
+        expY[k] = (int32_t)eX[ordY[k]];
+        memcpy(&coef[32 * (size_t)k], coeff32 + 32 * (size_t)ordX[k], 32);
+        memcpy(&coef[32 * ((size_t)nl + k)], coeff32 + 32 * (size_t)ordY[k], 32);
     }
-    nvtxRangePop();
-    return SONIC_OK;
+    uint32_t* d_ptrX = ar.get<uint32_t>(xlen + 1);
+    uint32_t* d_ptrY = ar.get<uint32_t>(ylen + 1);
+    int32_t* d_expX = ar.get<int32_t>(nl ? nl : 1);
+    int32_t* d_expY = ar.get<int32_t>(nl ? nl : 1);
+    Fr* d_coef_c = ar.get<Fr>(2 * (size_t)(nl ? nl : 1));
+    Fr* d_coef = ar.get<Fr>(2 * (size_t)(nl ? nl : 1));
+    SONIC_CUDA(cudaMemcpyAsync(d_ptrX, ptrX.data(), 4 * (size_t)(xlen + 1), cudaMemcpyHostToDevice, st));
+    SONIC_CUDA(cudaMemcpyAsync(d_ptrY, ptrY.data(), 4 * (size_t)(ylen + 1), cudaMemcpyHostToDevice, st));
+    if (nl) {
+        SONIC_CUDA(cudaMemcpyAsync(d_expX, expX.data(), 4 * (size_t)nl, cudaMemcpyHostToDevice, st));
+        SONIC_CUDA(cudaMemcpyAsync(d_expY, expY.data(), 4 * (size_t)nl, cudaMemcpyHostToDevice, st));
+        SONIC_CUDA(cudaMemcpyAsync(d_coef_c, coef.data(), 64 * (size_t)nl, cudaMemcpyHostToDevice, st));
+        fr_to_mont(cx, d_coef_c, d_coef, 2 * (size_t)nl, bad);
+    }
+    SONIC_CUDA(cudaStreamSynchronize(st));   // the host vectors above are large and pageable: do not let them die in flight
+
+    // ---- evaluation points y_j, z_j, u, v and their power tables ------------------------------------------------
+    const uint32_t nr = 2 * M + 8, np = 2 * M + 5;
+    const uint32_t PT_YJ = 3, PT_ZJ = 3 + M, PT_U = 3 + 2 * M, PT_V = 4 + 2 * M;
+    Fr* rnd_m = ar.get<Fr>(nr);
+    fr_to_mont(cx, d_rnd, rnd_m, nr, bad);
+    Fr* pts = ar.get<Fr>(2 * np);
+    const uint64_t tl = (uint64_t)std::max(xlen, ylen) + 2;   // the openings index z^k for every slot k of a window
+    Fr* tabs = ar.get<Fr>(2 * (size_t)np * tl);
+    {
+        std::vector<uint32_t> h;
+        for (uint32_t p = 3; p < np; ++p) h.push_back(p);
+        const uint32_t ns = (uint32_t)h.size();
+        for (uint32_t k = 0; k < ns; ++k) h.push_back(h[k]);
+        for (uint32_t k = 0; k < ns; ++k) h.push_back(np + h[k]);
+        uint32_t* d_sel = ar.get<uint32_t>(h.size());
+        SONIC_CUDA(cudaMemcpyAsync(d_sel, h.data(), 4 * h.size(), cudaMemcpyHostToDevice, st));
+        SONIC_LAUNCH(k_prove_points, ns, 32, 0, rnd_m, M, 0, d_sel, pts);
+        pow_tables(cx, pts, (int)(2 * ns), tabs, tl, tl, d_sel + ns);
+    }
+    auto fwd = [&](uint32_t p) { return tabs + (size_t)p * tl; };
+    auto inv = [&](uint32_t p) { return tabs + (size_t)(np + p) * tl; };
+
+    // ---- s(X, y_j) and s(u, Y) ------------------------------------------------------------------------------------
+    Fr* sxy_m = ar.get<Fr>((size_t)(M ? M : 1) * xlen);
+    Fr* sxy_c = ar.get<Fr>((size_t)(M ? M : 1) * xlen);
+    if (M) {
+        std::vector<uint32_t> h(2 * (size_t)M);
+        for (uint32_t j = 0; j < M; ++j) { h[j] = PT_YJ + j; h[M + j] = np + PT_YJ + j; }
+        uint32_t* d_idx = ar.get<uint32_t>(2 * (size_t)M);
+        SONIC_CUDA(cudaMemcpyAsync(d_idx, h.data(), 8 * (size_t)M, cudaMemcpyHostToDevice, st));
+        SONIC_LAUNCH(k_eval_term_rows, dim3(div_up(xlen, 128), M), 128, 0, TermRows{d_ptrX, d_expX, d_coef}, xlen, tabs, tl, d_idx, d_idx + M, sxy_m, xlen);
+        fr_from_mont(cx, sxy_m, sxy_c, (size_t)M * xlen);
+    }
+    Window suy;
+    suy.lo = ylo;
+    suy.len = ylen;
+    suy.mont = ar.get<Fr>(ylen);
+    suy.canon = ar.get<Fr>(ylen);
+    {
+        const uint32_t h[2] = {PT_U, np + PT_U};
+        uint32_t* d_idx = ar.get<uint32_t>(2);
+        SONIC_CUDA(cudaMemcpyAsync(d_idx, h, 8, cudaMemcpyHostToDevice, st));
+        SONIC_LAUNCH(k_eval_term_rows, dim3(div_up(ylen, 128), 1), 128, 0, TermRows{d_ptrY, d_expY, d_coef + nl}, ylen, tabs, tl, d_idx, d_idx + 1, suy.mont, ylen);
+        fr_from_mont(cx, suy.mont, suy.canon, ylen);
+    }
+    auto sxy = [&](uint32_t j) { Window w; w.mont = sxy_m + (size_t)j * xlen; w.canon = sxy_c + (size_t)j * xlen; w.lo = xlo; w.len = xlen; return w; };
+
+    // ---- openings (Signature.hs:43,54-55,63) and the MSM list in record order -----------------------------------------
+    std::vector<OpenJob> ojobs;
+    Fr* scratch = ar.get<Fr>((size_t)M + 2);
+    uint32_t nscratch = 0;
+    struct Quot { Fr* q; int64_t lo; uint32_t len; };
+    auto add_open = [&](const Window& f, const Fr* pz, const Fr* pzi, Fr* value_slot) -> Quot {
+        OpenJob jb;
+        jb.f = f.mont; jb.pz = pz; jb.pzi = pzi;
+        jb.q_canon = ar.get<Fr>(f.len);
+        jb.value_canon = value_slot ? value_slot : scratch + nscratch++;
+        jb.len = f.len; jb.lo = (int32_t)f.lo; jb.z_is_zero = 0; jb.pad = 0;
+        ojobs.push_back(jb);
+        return Quot{jb.q_canon, f.lo, f.len - 1};
+    };
+    std::vector<Quot> q_wj(M), q_wpj(M), q_qj(M);
+    for (uint32_t j = 0; j < M; ++j) {
+        q_wj[j] = add_open(sxy(j), fwd(PT_ZJ + j), inv(PT_ZJ + j), d_vals + j);
+        q_wpj[j] = add_open(sxy(j), fwd(PT_U), inv(PT_U), nullptr);
+        q_qj[j] = add_open(suy, fwd(PT_YJ + j), inv(PT_YJ + j), d_vals + M + j);
+    }
+    const Quot q_v = add_open(suy, fwd(PT_V), inv(PT_V), nullptr);
+    open_batch(cx, ojobs);
+    std::vector<ProofMsm> pm;
+    auto commit = [&](const Window& f) { pm.push_back(ProofMsm{SONIC_FAMILY_ALPHA, f.canon, f.lo, f.len, true}); };   // max = d: no shift
+    auto opening = [&](const Quot& q) { pm.push_back(ProofMsm{SONIC_FAMILY_PLAIN, q.q, q.lo, q.len, false}); };
+    for (uint32_t j = 0; j < M; ++j) { commit(sxy(j)); opening(q_wj[j]); }
+    for (uint32_t j = 0; j < M; ++j) { opening(q_wpj[j]); opening(q_qj[j]); }
+    opening(q_v);
+    commit(suy);
+    std::vector<int64_t> piece_lo(pm.size()), piece_hi(pm.size());
+    for (size_t i = 0; i < pm.size(); ++i) {
+        piece_lo[i] = std::max(pm[i].lo, -d);
+        piece_hi[i] = std::max(piece_lo[i], std::min(pm[i].lo + (int64_t)pm[i].len, d + 1));
+    }
+    return enqueue_msms(cx, srs, pm, piece_lo, piece_hi, viol, false, d_result);
 }
 
 void prove_collect_timing(Ctx& cx) {

@@ -130,3 +130,53 @@ def test_reference_arm_prints_the_contract_line():
     quiet = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                            capture_output=True, text=True, env=env, timeout=300)
     assert quiet.returncode == 0 and quiet.stdout.strip() == ""
+
+
+def test_python_mirror_checks_shapes_before_any_pointer_crosses():
+    """The C side copies Q*n (and Q, n, 2Q+8) field elements from the buffers it is handed: ragged weight rows, a short
+    cs, a short assignment or a short list of draws must be refused by the mirror itself (no GPU needed to see it)."""
+    import sonic_b200 as sb
+
+    ok = [[1, 2, 3], [4, 5, 6]]
+    for wL, wR, wO, cs in (([[1, 2, 3], [4, 5]], ok, ok, [1, 2]),        # ragged row
+                           (ok, [[1, 2, 3]], ok, [1, 2]),                 # wR has fewer rows
+                           (ok, ok, [[1, 2], [3, 4]], [1, 2]),            # wO is narrower
+                           (ok, ok, ok, [1])):                            # cs too short
+        with pytest.raises(sb.SonicError) as e:
+            sb.ArithCircuit(sb.GateWeights(wL, wR, wO), cs).handle()
+        assert e.value.kind == "INVALID_ARG"
+    with pytest.raises(sb.SonicError) as e:
+        sb.ArithCircuit(sb.GateWeights([], [], []), []).handle()
+    assert e.value.text == "Empty weights"
+
+    class FakeHandle:
+        n, Q = 3, 2
+
+    from sonic_b200 import api
+
+    good = sb.Assignment([1, 2, 3], [1, 2, 3], [1, 4, 9])
+    api._check_prove_inputs(FakeHandle, good, list(range(1, 13)))
+    for a, r in ((sb.Assignment([1, 2], [1, 2, 3], [1, 4, 9]), list(range(1, 13))), (good, list(range(1, 12)))):
+        with pytest.raises(sb.SonicError):
+            api._check_prove_inputs(FakeHandle, a, r)
+
+
+def test_header_compiles_as_strict_c11_and_the_consumer_links():
+    """tests/c/abi_multi.c names every prototype of include/sonic_b200.h with its full type and is built with
+    -std=c11 -Wall -Wextra -Werror against the library: a declaration drifting from the definition (or from what a
+    `foreign import ccall` would bind) stops the build.  Running it needs GPUs (tests/test_gpu_multi.py)."""
+    import subprocess
+
+    cdir = os.path.join(ROOT, "tests", "c")
+    subprocess.run(["make", "-C", cdir, "-B", "abi_multi"], check=True, capture_output=True, text=True)
+    assert os.path.exists(os.path.join(cdir, "abi_multi"))
+    # the table in the C file covers the header: same symbol set
+    text = open(os.path.join(cdir, "abi_multi.c")).read()
+    for name in _declared_symbols():
+        assert re.search(r"\b%s\b" % name, text), f"{name} is not referenced by tests/c/abi_multi.c"
+    # without a GPU the program fails loudly with the library's own message
+    import torch
+
+    if not torch.cuda.is_available():
+        out = subprocess.run([os.path.join(cdir, "abi_multi"), "1", "4"], capture_output=True, text=True)
+        assert out.returncode == 2 and "no CPU fallback" in out.stderr

@@ -137,18 +137,39 @@ def test_config2_prove_n4096_matches_reference_algorithm(gpu):
     assert e.value.text == f"Parameter d is not large enough: {d2} should be greater than {7 * n}"
 
 
-def test_config4_prove_n65536_verifies(gpu):
-    """BASELINE config 4: n = 2^16, Q = 8, d = 7n.  verify(prove(...)) == True (pcV in the exponent
-    with the trapdoor), two proofs with the same draws are identical, and R, T satisfy the
-    commitment identities."""
+def test_config4_prove_n65536_byte_exact_and_verifies(gpu):
+    """BASELINE config 4 (the headline): n = 2^16, Q = 8, d = 7n.  The proof equals, byte for byte, the one the C
+    restatement of the reference algorithm produced for the same inputs (tests/golden/prove_config4.json, generated by
+    tools/gen_golden_large.py: per-term double-and-add MSMs and a schoolbook t(X,y) -- no bucket method, no NTT, 26 CPU
+    minutes), so the n = 2^16 branches of the CUDA path (NTT length 2^19, 10 sort tiles per SM, 65 536-entry buckets
+    through k_msm_heavy, multi-wave accumulation) are pinned, not only self-consistent.  Sampled SRS elements at this d
+    are pinned by the same file.  Then verify(prove(...)) == True (pcV in the exponent with the trapdoor), the
+    commitment identities of R, A, B, and the same bytes from 2, 3 and 8 shards."""
+    import hashlib
+    import json
+    import os
+
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prove_config4.json")))
     n, Q = 1 << 16, 8
     d = 7 * n
+    assert (gold["n"], gold["Q"], gold["d"], gold["circuit_seed"], gold["rnd_seed"]) == (n, Q, d, 4, 40)
     x, alpha = synth.trapdoor()
     c = synth.synthetic_circuit_bytes(n, Q, seed=4)
     rnd = [v or 1 for v in synth.fr_ints(40, 2 * Q + 8)]
     srs = gpu.SRS.new(d, x, alpha)
+    for key, raw_hex in gold["srs_raw96_hex"].items():
+        fam, k = (int(v) for v in key.split(":"))
+        if fam == 1 and k == 0:
+            continue   # g^alpha is not part of the SRS (SRS.hs:38): the raw table holds zeros there
+        raw = bytes.fromhex(raw_hex)
+        pt = (int.from_bytes(raw[:48], "little"), int.from_bytes(raw[48:], "little"))
+        assert srs.g1(fam, k) == C(pt), key
     got = _prove_bytes(gpu, srs, c, rnd)
+    assert hashlib.sha256(got).hexdigest() == gold["proof_sha256"]
+    assert got == bytes.fromhex(gold["proof_hex"])
     assert got == _prove_bytes(gpu, srs, c, rnd)
+    for world in (2, 3, 8):
+        assert _prove_sharded_bytes(gpu, srs, c, rnd, world) == got, world
     proof = S.decode_proof(got, Q)
     ints = c["ints"]
     one_row = lambda row: [[1] * n if q == row else [0] * n for q in range(Q)]
