@@ -275,10 +275,15 @@ double sonic_imad_peak_lmacs(int variant, int iters);
 /* Device self-tests of the arithmetic layer (raw Montgomery-form limbs, little-endian u32):
  * field 0 = Fq (12 limbs), 1 = Fr (8 limbs); op 0 mul, 1 add, 2 sub, 3 to_mont, 4 from_mont,
  * 5 inv, 6 sqr, 7 neg, 8 inv by binary Euclid (the MSM's final to-affine).  G1: points as XYZZ (48 limbs); op 0 acc+affine(b.x,b.y), 1 acc+b, 2 2*acc,
- * 3 2*affine(a.x,a.y); outputs affine (24 limbs) and the compressed encoding. */
+ * 3 2*affine(a.x,a.y), 4 acc+b and 5 2*acc by a quad of lanes; outputs affine (24 limbs) and the compressed encoding. */
 int sonic_selftest_field(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out, uint32_t n);
 int sonic_selftest_g1(int op, const uint32_t* a_xyzz, const uint32_t* b_xyzz, uint32_t* out_affine,
                       uint8_t* out_comp, uint32_t n);
+/* Latency probe: ns per operation of a chain of `iters` dependent operations run by every thread of
+ * blocks x threads (one warp per SM = what a lone warp of the MSM's tail stages sees).
+ * op 0 Fq multiplication, 1 full addition, 2 doubling, 3 mixed addition, 4 / 5 addition / doubling shared by a
+ * quad of lanes (csrc/g1coop.cuh).  sonic_selftest_g1 ops 4 / 5 check those against ops 1 / 2. */
+double sonic_selftest_latency_ns(int op, int iters, int blocks, int threads);
 /* device memory helpers for harnesses that have no CUDA binding of their own */
 int sonic_dev_alloc(uint64_t bytes, void** out);
 int sonic_dev_free(void* p);

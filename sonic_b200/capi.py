@@ -79,6 +79,7 @@ SYMBOLS = {
     "sonic_imad_peak_lmacs": (c_double, [c_int, c_int]),
     "sonic_selftest_field": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, ctypes.c_uint32]),
     "sonic_selftest_g1": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_uint32]),
+    "sonic_selftest_latency_ns": (c_double, [c_int, c_int, c_int, c_int]),
     "sonic_dev_alloc": (c_int, [c_uint64, POINTER(c_void_p)]),
     "sonic_dev_free": (c_int, [c_void_p]),
     "sonic_dev_upload": (c_int, [c_void_p, c_void_p, c_uint64]),

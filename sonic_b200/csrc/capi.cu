@@ -1565,7 +1565,7 @@ int sonic_set_option(const char* name, int64_t value) {
         if (value < 0) return fail(SONIC_ERR_INVALID_ARG, "budget must be >= 0");
         each([&](Ctx& cx) { cx.opt_precompute_budget = (uint64_t)value << 20; });
     } else if (!strcmp(name, "reduce_mode")) {
-        if (value < 0 || value > 1) return fail(SONIC_ERR_INVALID_ARG, "reduce_mode must be 0 or 1");
+        if (value < 0 || value > 3) return fail(SONIC_ERR_INVALID_ARG, "reduce_mode must be 0 (automatic), 1 (level by level), 2 (thread per K buckets) or 3 (quads of lanes)");
         each([&](Ctx& cx) { cx.opt_reduce_mode = (int)value; });
     } else if (!strcmp(name, "sort_mode")) {
         // 0: thread per term + global atomics; 1: tiled counting sort, automatic tile count; 2..64: tiled, that many tiles per SM
@@ -1665,6 +1665,16 @@ int sonic_selftest_field(int field, int op, const uint32_t* a, const uint32_t* b
 int sonic_selftest_g1(int op, const uint32_t* a_xyzz, const uint32_t* b_xyzz, uint32_t* out_affine, uint8_t* out_comp, uint32_t n) {
     if (!a_xyzz || !b_xyzz || !out_affine || !out_comp) return fail(SONIC_ERR_INVALID_ARG, "bad argument");
     return guarded([&](Ctx& cx) { return selftest_g1(cx, op, a_xyzz, b_xyzz, out_affine, out_comp, n); });
+}
+
+double sonic_selftest_latency_ns(int op, int iters, int blocks, int threads) {
+    if (op < 0 || op > 5 || iters < 1 || iters > (1 << 20) || blocks < 1 || blocks > (1 << 16) || threads < 1 || threads > 1024 || (threads & 31)) return -1.0;
+    double ns = -1.0;
+    guarded([&](Ctx& cx) {
+        ns = selftest_latency_ns(cx, op, iters, blocks, threads);
+        return (int)SONIC_OK;
+    });
+    return ns;
 }
 
 int sonic_dev_alloc(uint64_t bytes, void** out) {

@@ -118,7 +118,7 @@ struct Ctx {
     int opt_chunk = 0;
     int opt_acc_mode = 1;                                 // 0 straight-line mixed addition in registers, 1 compact (operand file in shared memory)
     bool opt_g2 = false;                                  // SRS.new also generates the G2 h-vectors
-    int opt_reduce_mode = 0;                              // 0 flat (K buckets per thread + block tree), 1 level by level
+    int opt_reduce_mode = 0;                              // 0 automatic (quads of lanes while latency-bound, else thread per K buckets), 1 level by level, 2 thread per K buckets, 3 quads
     int opt_sort_mode = 1;                                // 0 thread per term + global atomics, 1 tiled counting sort (shared-memory histograms)
     bool sort_smem_set = false;
     int opt_reduce_k = 0;                                 // buckets per thread in the flat reduction (0 = automatic)

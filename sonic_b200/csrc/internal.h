@@ -83,6 +83,7 @@ int selftest_field(Ctx& cx, int which, int op, const void* a, const void* b, voi
 int pcv_fold(Ctx& cx, uint32_t k, const uint8_t* F48, const uint8_t* W48, const uint8_t* v32, const uint8_t* z32,
              const uint8_t* r32, const uint32_t* group, uint32_t ngroups, uint8_t* out48);
 int selftest_g1(Ctx& cx, int op, const void* a, const void* b, void* out_aff, void* out_comp, uint32_t n);
+double selftest_latency_ns(Ctx& cx, int op, int iters, int blocks, int threads);
 
 // ---- resident SRS, one replica per device --------------------------------------------------
 // Device layout: one array of affine points indexed by exponent,

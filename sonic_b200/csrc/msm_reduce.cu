@@ -2,6 +2,7 @@
 // chunk borders, reduce every bucket set to sum_b (b+1) * B_b, and finish each job (fold, one
 // inversion, affine + compressed encoding).
 #include "msm_acc.cuh"
+#include "g1coop.cuh"
 
 namespace sonic {
 
@@ -152,6 +153,94 @@ k_msm_bucket_reduce(const G1XYZZ* __restrict__ buckets, uint32_t B, uint32_t K, 
     if (threadIdx.x == 0) store_xyzz(partial + (size_t)window * gridDim.x + blockIdx.x, acc);
 }
 
+// ---- stage 6, quad variant (the default): the same K-buckets-per-worker running sums, but a worker is a QUAD of
+// lanes sharing every point operation (g1coop.cuh).  The stage is a chain of dependent full additions --
+// 2K running-sum steps, the offset multiple first * (sum of the K buckets) (15 doublings + a few additions), the
+// block tree -- whose length barely depends on K, and a lone thread spends ~20 us on each link (14 dependent
+// multiplications at ~2 800 cycles: the carry chains of one multiplication cannot overlap).  A quad brings a
+// link down to 4.5 multiplication latencies (add) / 3.5 (double).  Measured for one job of 2^15 buckets:
+// 0.74 ms -> see profiles/r02*_others_ncu.md.
+// The running sum and the multiple live in registers; the weighted accumulator is parked in shared memory (one
+// slot per quad, read by all four lanes as a broadcast) so that two points are live at a time.
+constexpr int RQ_THREADS = 128;
+constexpr int RQ_QUADS = RQ_THREADS / 4;
+constexpr int RQ_MINB = 2;
+
+__global__ void __launch_bounds__(RQ_THREADS, RQ_MINB)
+k_msm_bucket_reduce_quad(const G1XYZZ* __restrict__ buckets, uint32_t B, uint32_t K, G1XYZZ* __restrict__ partial) {
+    __shared__ G1XYZZ park[RQ_QUADS];
+    const Quad q;
+    const uint32_t window = blockIdx.y;
+    const uint32_t qi = threadIdx.x >> 2;
+    const uint32_t first = (blockIdx.x * RQ_QUADS + qi) * K;  // 0-based bucket index in window
+    if (q.lane == 0) park[qi] = G1XYZZ::inf();
+    __syncwarp(q.mask);
+    if (first < B) {
+        G1XYZZ run = G1XYZZ::inf();
+        const G1XYZZ* bp = buckets + (size_t)window * B + first;
+        const uint32_t kmax = (B - first < K) ? (B - first) : K;
+        for (uint32_t k = kmax; k-- > 0;) {
+            g1_add_quad(q, run, load_xyzz(bp + k));
+            G1XYZZ acc = park[qi];
+            g1_add_quad(q, acc, run);
+            __syncwarp(q.mask);
+            if (q.lane == 0) park[qi] = acc;
+            __syncwarp(q.mask);
+        }
+        // weights are (bucket index + 1): add first * (sum of the K buckets)
+        if (first) {
+            G1XYZZ m = G1XYZZ::inf();
+            for (int bit = 31 - __clz(first); bit >= 0; --bit) {
+                m = g1_dbl_quad(q, m);
+                if ((first >> bit) & 1) g1_add_quad(q, m, run);
+            }
+            G1XYZZ acc = park[qi];
+            g1_add_quad(q, acc, m);
+            __syncwarp(q.mask);
+            if (q.lane == 0) park[qi] = acc;
+            __syncwarp(q.mask);
+        }
+    }
+    // tree over the quads of the block
+    __syncthreads();
+    for (uint32_t s = RQ_QUADS / 2; s > 0; s >>= 1) {
+        G1XYZZ acc;
+        if (qi < s) {
+            acc = park[qi];
+            g1_add_quad(q, acc, park[qi + s]);
+        }
+        __syncthreads();
+        if (qi < s && q.lane == 0) park[qi] = acc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) store_xyzz(partial + (size_t)window * gridDim.x + blockIdx.x, park[0]);
+}
+
+// ---- stage 7, quad variant, one bucket set per job (window tables): fold the S block partials, one
+// inversion, affine + compressed
+__global__ void __launch_bounds__(RQ_THREADS)
+k_msm_finish_quad(const G1XYZZ* __restrict__ partial, uint32_t S, G1Affine* __restrict__ out_aff, uint8_t* __restrict__ out_comp) {
+    __shared__ G1XYZZ park[RQ_QUADS];
+    const Quad q;
+    const uint32_t job = blockIdx.x, qi = threadIdx.x >> 2;
+    const G1XYZZ* pp = partial + (size_t)job * S;
+    G1XYZZ v = G1XYZZ::inf();
+    for (uint32_t s = qi; s < S; s += RQ_QUADS) g1_add_quad(q, v, load_xyzz(pp + s));
+    if (q.lane == 0) park[qi] = v;
+    __syncthreads();
+    for (uint32_t s = RQ_QUADS / 2; s > 0; s >>= 1) {
+        if (qi < s) g1_add_quad(q, v, park[qi + s]);
+        __syncthreads();
+        if (qi < s && q.lane == 0) park[qi] = v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        G1Affine a = g1_to_affine_single(v);
+        if (out_aff) out_aff[job] = a;
+        if (out_comp) g1_compress(a, out_comp + (size_t)job * 48);
+    }
+}
+
 // ---- stage 7: per job: fold window partials, Horner over windows, affine, compress ---------
 __global__ void __launch_bounds__(64)
 k_msm_finish(const G1XYZZ* __restrict__ partial, uint32_t S, int W, int c, G1Affine* __restrict__ out_aff,
@@ -200,7 +289,29 @@ void msm_reduce_stage(Ctx& cx, const MsmPlan& p, int M, const uint32_t* offsets,
     SONIC_LAUNCH(k_msm_heavy, cx.sm_count * 2, MSM_RED_THREADS, 0, offsets, p.L, buckets, head, tail, heavy_count, heavy_list);
     SONIC_CUDA(cudaEventRecord(cx.ev[2], st));
 
-    if (cx.opt_reduce_mode == 0) {
+    // Automatic (reduce_mode 0): quads while the stage is latency-bound -- few bucket sets: a standalone MSM, a small
+    // proof, one rank's share of a sharded proof (one job of 2^15 buckets: 0.97 -> 0.55 ms; prove at n = 2^13: 1.33 -> 0.95) --
+    // and one thread per K buckets once there are enough buckets to fill the multiplier pipe without help (39 sets of
+    // 2^15: 2.58 ms against 2.74 with quads).
+    const bool quads = cx.opt_reduce_mode == 3 || (cx.opt_reduce_mode == 0 && (uint64_t)M * p.sets * p.B <= (1ull << 19));
+    if (quads) {
+        // quads of lanes share every point operation.  K buckets per quad, as large as keeping ALL blocks
+        // resident at once allows (RQ_MINB per SM): a second wave would double the time of this latency-bound stage.
+        const uint32_t nsets = (uint32_t)M * p.sets;
+        uint32_t K = (uint32_t)cx.opt_reduce_k;
+        if (K == 0) {
+            uint32_t S_max = (uint32_t)cx.sm_count * RQ_MINB / nsets;
+            if (S_max < 1) S_max = 1;
+            K = div_up(p.B, (uint64_t)RQ_QUADS * S_max);
+            if (K < 2) K = 2;
+        }
+        if (K > p.B) K = p.B;
+        const uint32_t S = div_up(p.B, (uint64_t)RQ_QUADS * K);
+        G1XYZZ* partial = ar.get<G1XYZZ>((size_t)nsets * S);
+        SONIC_LAUNCH(k_msm_bucket_reduce_quad, dim3(S, nsets), RQ_THREADS, 0, buckets, p.B, K, partial);
+        if (p.sets == 1) SONIC_LAUNCH(k_msm_finish_quad, M, RQ_THREADS, 0, partial, S, d_out_aff, d_out_comp);
+        else SONIC_LAUNCH(k_msm_finish, M, 64, 0, partial, S, p.sets, p.c, d_out_aff, d_out_comp);
+    } else if (cx.opt_reduce_mode != 1) {
         // flat: each thread K buckets + its offset multiple, block tree, per-job fold of the block partials
         // buckets per thread: every thread pays ~29 extra point operations (its offset multiple and
         // the block tree) on top of 2 per bucket, so K is as large as filling the machine allows

@@ -2,6 +2,7 @@
 // parity tests can localise a failure below the MSM (tests/test_gpu_arith.py).
 #include "internal.h"
 #include "g1io.cuh"
+#include "g1coop.cuh"
 
 namespace sonic {
 
@@ -43,6 +44,65 @@ __global__ void k_selftest_g1(int op, const G1XYZZ* __restrict__ a, const G1XYZZ
     g1_compress(o, comp + (size_t)i * 48);
 }
 
+// the same through the quad-cooperative formulas (g1coop.cuh): four lanes per element.  op 4 add, 5 dbl
+__global__ void k_selftest_g1_quad(int op, const G1XYZZ* __restrict__ a, const G1XYZZ* __restrict__ b, G1Affine* __restrict__ out,
+                                   uint8_t* __restrict__ comp, uint32_t n) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    if (i >= n) return;   // n is padded to a multiple of 8 elements by the launcher: whole warps stay together
+    const Quad q;
+    G1XYZZ r = load_xyzz(a + i);
+    if (op == 4) g1_add_quad(q, r, load_xyzz(b + i));
+    else r = g1_dbl_quad(q, r);
+    if (q.lane == 0) {
+        G1Affine o = g1_to_affine(r);
+        out[i] = o;
+        g1_compress(o, comp + (size_t)i * 48);
+    }
+}
+
+// Latency probe: every thread runs a chain of `iters` DEPENDENT operations; with one warp per block and
+// one block per SM the time per operation is the latency a lone warp sees (the regime of the MSM's tail).
+//   0 fp_mul (Fq)   1 g1_add   2 g1_dbl   3 g1_madd   4 g1_add_quad   5 g1_dbl_quad
+__global__ void k_latency(int op, int iters, const G1XYZZ* __restrict__ seed, G1XYZZ* __restrict__ sink) {
+    G1XYZZ acc = load_xyzz(seed), b = load_xyzz(seed + 1);
+    G1Affine ba;
+    ba.x = b.x;
+    ba.y = b.y;
+    const Quad q;
+    for (int i = 0; i < iters; ++i) {
+        switch (op) {
+            case 0: acc.x = fp_mul(acc.x, b.x); break;
+            case 1: g1_add(acc, b); break;
+            case 2: acc = g1_dbl(acc); break;
+            case 3: g1_madd(acc, ba); break;
+            case 4: g1_add_quad(q, acc, b); break;
+            default: acc = g1_dbl_quad(q, acc); break;
+        }
+    }
+    if (threadIdx.x == 0) store_xyzz(sink + blockIdx.x, acc);
+}
+
+double selftest_latency_ns(Ctx& cx, int op, int iters, int blocks, int threads) {
+    G1XYZZ h[2];
+    h[0] = G1XYZZ::from_affine(G1Affine::gen());
+    h[1] = g1_dbl(g1_dbl(h[0]));   // 4G in XYZZ with ZZ != 1 (host build of the same headers)
+    G1XYZZ* seed = cx.arena.get<G1XYZZ>(2);
+    G1XYZZ* sink = cx.arena.get<G1XYZZ>(blocks);
+    SONIC_CUDA(cudaMemcpyAsync(seed, h, sizeof h, cudaMemcpyHostToDevice, cx.stream));
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        SONIC_CUDA(cudaEventRecord(cx.ev[4], cx.stream));
+        SONIC_LAUNCH(k_latency, blocks, threads, 0, op, iters, seed, sink);
+        SONIC_CUDA(cudaEventRecord(cx.ev[5], cx.stream));
+        SONIC_CUDA(cudaStreamSynchronize(cx.stream));
+        float ms = 0;
+        SONIC_CUDA(cudaEventElapsedTime(&ms, cx.ev[4], cx.ev[5]));
+        const double ns = (double)ms * 1e6 / iters;
+        if (rep == 0 || ns < best) best = ns;
+    }
+    return best;
+}
+
 int selftest_field(Ctx& cx, int which, int op, const void* a, const void* b, void* out, uint32_t n) {
     const size_t esz = which == 0 ? sizeof(Fq) : sizeof(Fr);
     char* da = cx.arena.get<char>(esz * n);
@@ -64,7 +124,8 @@ int selftest_g1(Ctx& cx, int op, const void* a, const void* b, void* out_aff, vo
     uint8_t* dcomp = cx.arena.get<uint8_t>((size_t)n * 48);
     SONIC_CUDA(cudaMemcpyAsync(da, a, sizeof(G1XYZZ) * n, cudaMemcpyHostToDevice, cx.stream));
     SONIC_CUDA(cudaMemcpyAsync(db, b, sizeof(G1XYZZ) * n, cudaMemcpyHostToDevice, cx.stream));
-    SONIC_LAUNCH(k_selftest_g1, div_up(n, 64), 64, 0, op, da, db, dout, dcomp, n);
+    if (op >= 4) SONIC_LAUNCH(k_selftest_g1_quad, div_up((uint64_t)n * 4, 64), 64, 0, op, da, db, dout, dcomp, n);
+    else SONIC_LAUNCH(k_selftest_g1, div_up(n, 64), 64, 0, op, da, db, dout, dcomp, n);
     SONIC_CUDA(cudaMemcpyAsync(out_aff, dout, sizeof(G1Affine) * n, cudaMemcpyDeviceToHost, cx.stream));
     SONIC_CUDA(cudaMemcpyAsync(out_comp, dcomp, (size_t)n * 48, cudaMemcpyDeviceToHost, cx.stream));
     SONIC_CUDA(cudaStreamSynchronize(cx.stream));

@@ -74,6 +74,7 @@ typedef struct {
     double (*imad_peak_lmacs)(int, int);
     int (*selftest_field)(int, int, const uint32_t*, const uint32_t*, uint32_t*, uint32_t);
     int (*selftest_g1)(int, const uint32_t*, const uint32_t*, uint32_t*, uint8_t*, uint32_t);
+    double (*selftest_latency_ns)(int, int, int, int);
     int (*dev_alloc)(uint64_t, void**);
     int (*dev_free)(void*);
     int (*dev_upload)(void*, const void*, uint64_t);
@@ -88,7 +89,7 @@ static const sonic_abi ABI = {
     sonic_shard_blob_size, sonic_prove_shard, sonic_prove_combine, sonic_prove_shard_sink, sonic_prove_combine_device,
     sonic_prove_device, sonic_prove_shard_device, sonic_hsc_prove, sonic_hsc_prove_terms, sonic_pcv_fold, sonic_set_option,
     sonic_last_timing_ms, sonic_last_timing_ms_dev, sonic_launch_count, sonic_bench_mark, sonic_bench_elapsed_ms,
-    sonic_imad_peak_lmacs, sonic_selftest_field, sonic_selftest_g1, sonic_dev_alloc, sonic_dev_free, sonic_dev_upload, sonic_dev_download,
+    sonic_imad_peak_lmacs, sonic_selftest_field, sonic_selftest_g1, sonic_selftest_latency_ns, sonic_dev_alloc, sonic_dev_free, sonic_dev_upload, sonic_dev_download,
 };
 
 /* ---- deterministic inputs -------------------------------------------------------------------------- */
