@@ -514,20 +514,15 @@ void free_srs_rep(SrsRep* s) {
     delete s;
 }
 
-// every level of the resident array, slice by slice: device q broadcasts its slice of each level
-void allgather_levels(int r, Ctx& cx, G1Affine* points, uint64_t npts, uint64_t levels) {
+// The resident array (all levels, one flat array) is dealt in equal chunks of srs_chunk() points, device r
+// generating chunk r; ONE in-place ncclAllGather replicates it (the array is allocated with the padding
+// the last chunk may need).
+uint64_t srs_chunk(uint64_t total, int ndev) { return (total + (uint64_t)ndev - 1) / (uint64_t)ndev; }
+
+void allgather_points(int r, Ctx& cx, G1Affine* points, uint64_t total) {
     Runtime& R = rt();
-    for (uint64_t j = 0; j < levels; ++j) {
-        SONIC_NCCL(ncclGroupStart());
-        for (int q = 0; q < R.ndev; ++q) {
-            const uint64_t a = npts * q / R.ndev, b = npts * (q + 1) / R.ndev;
-            if (b > a) {
-                G1Affine* p = points + j * npts + a;
-                SONIC_NCCL(ncclBroadcast(p, p, (b - a) * sizeof(G1Affine), ncclUint8, q, R.comm[r], cx.stream));
-            }
-        }
-        SONIC_NCCL(ncclGroupEnd());
-    }
+    const uint64_t chunk = srs_chunk(total, R.ndev);
+    SONIC_NCCL(ncclAllGather(points + (uint64_t)r * chunk, points, chunk * sizeof(G1Affine), ncclUint8, R.comm[r], cx.stream));
 }
 
 void shutdown_locked() {
@@ -732,7 +727,8 @@ int sonic_srs_new(uint64_t d, const uint8_t x[32], const uint8_t alpha[32], soni
         rep->tables.W = pre_c > 0 ? (int)levels : 0;
         rep->tables.stride = (uint32_t)npts;
         int rc = attempt(cx, [&]() -> int {
-            SONIC_CUDA(cudaMalloc((void**)&rep->points, npts * levels * sizeof(G1Affine)));
+            // (+ ndev points: the last chunk of the all-gather may reach past the end)
+            SONIC_CUDA(cudaMalloc((void**)&rep->points, (npts * levels + (uint64_t)R.ndev) * sizeof(G1Affine)));
             if (want_g2) SONIC_CUDA(cudaMalloc(&rep->g2_points, npts * g2_point_bytes()));
             Timer tm(cx);
             uint8_t* h = pinned(cx, 64);
@@ -740,15 +736,15 @@ int sonic_srs_new(uint64_t d, const uint8_t x[32], const uint8_t alpha[32], soni
             memcpy(h + 32, alpha, 32);
             Fr* d_canon = cx.arena.get<Fr>(2);
             SONIC_CUDA(cudaMemcpyAsync(d_canon, h, 64, cudaMemcpyHostToDevice, cx.stream));
-            const uint64_t a = npts * r / R.ndev, b = npts * (r + 1) / R.ndev;
-            srs_generate(cx, d, d_canon, rep->points, pre_c, a, b - a, rep->g2_points);
+            const uint64_t chunk = srs_chunk(npts * levels, R.ndev);
+            srs_generate(cx, d, d_canon, rep->points, pre_c, chunk * (uint64_t)r, chunk, rep->g2_points);
             SONIC_CUDA(cudaEventRecord(cx.ev[4], cx.stream));
             return (int)SONIC_OK;
         });
         if (R.ndev > 1) {
             if (!R.vote.all_ok(rc == SONIC_OK)) { nvtxRangePop(); return rc ? rc : fail(SONIC_ERR_CUDA, "SRS.new failed on another device"); }
             rc = attempt(cx, [&]() -> int {
-                allgather_levels(r, cx, rep->points, npts, levels);
+                allgather_points(r, cx, rep->points, npts * levels);
                 return (int)SONIC_OK;
             });
         }
@@ -1583,6 +1579,12 @@ int sonic_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "chunk")) {
         if (value < 0 || value > 4096) return fail(SONIC_ERR_INVALID_ARG, "chunk must be in [0, 4096]");
         each([&](Ctx& cx) { cx.opt_chunk = (int)value; });
+    } else if (!strcmp(name, "heavy_mode")) {
+        if (value < 0 || value > 1) return fail(SONIC_ERR_INVALID_ARG, "heavy_mode must be 0 or 1");
+        each([&](Ctx& cx) { cx.opt_heavy_mode = (int)value; });
+    } else if (!strcmp(name, "chunk_max")) {
+        if (value < 0 || value > 4096) return fail(SONIC_ERR_INVALID_ARG, "chunk_max must be in [0, 4096]");
+        each([&](Ctx& cx) { cx.opt_chunk_max = (int)value; });
     } else if (!strcmp(name, "shard_min_terms")) {
         if (value < 1) return fail(SONIC_ERR_INVALID_ARG, "shard_min_terms must be >= 1");
         R.opt_shard_min_terms = value;
@@ -1668,7 +1670,7 @@ int sonic_selftest_g1(int op, const uint32_t* a_xyzz, const uint32_t* b_xyzz, ui
 }
 
 double sonic_selftest_latency_ns(int op, int iters, int blocks, int threads) {
-    if (op < 0 || op > 5 || iters < 1 || iters > (1 << 20) || blocks < 1 || blocks > (1 << 16) || threads < 1 || threads > 1024 || (threads & 31)) return -1.0;
+    if (op < 0 || op > 8 || iters < 1 || iters > (1 << 20) || blocks < 1 || blocks > (1 << 16) || threads < 1 || threads > 1024 || (threads & 31)) return -1.0;
     double ns = -1.0;
     guarded([&](Ctx& cx) {
         ns = selftest_latency_ns(cx, op, iters, blocks, threads);

@@ -116,6 +116,8 @@ struct Ctx {
     uint64_t launches = 0;
     int opt_window_bits = 0;
     int opt_chunk = 0;
+    int opt_heavy_mode = 0;                               // 0 heavy buckets by quads in two steps, 1 one 128-thread block per heavy bucket
+    int opt_chunk_max = 0;                                // longest chunk the automatic rule may pick (0 = default)
     int opt_acc_mode = 1;                                 // 0 straight-line mixed addition in registers, 1 compact (operand file in shared memory)
     bool opt_g2 = false;                                  // SRS.new also generates the G2 h-vectors
     int opt_reduce_mode = 0;                              // 0 automatic (quads of lanes while latency-bound, else thread per K buckets), 1 level by level, 2 thread per K buckets, 3 quads

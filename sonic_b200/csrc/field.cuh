@@ -557,6 +557,16 @@ SONIC_HD Fp<P> fp_sqr(const Fp<P>& a) {
 #endif
 }
 
+// The same product as fp_mul through the wide path: the N^2 partial products first (rows independent of the
+// reduction, so more of them are in flight), then one Montgomery reduction.  Same IMAD count as the interleaved
+// CIOS; used where a lone warp waits on the latency of a multiplication rather than on the pipe (g1coop.cuh).
+template <class P>
+SONIC_HD Fp<P> fp_mul_wide(const Fp<P>& a, const Fp<P>& b) {
+    uint32_t T[2 * P::N];
+    wide_mul<P::N>(T, a.l, b.l);
+    return mont_reduce_wide<P>(T);
+}
+
 // canonical <-> Montgomery
 template <class P>
 SONIC_HD Fp<P> fp_to_mont(const Fp<P>& a) { return fp_mul(a, Fp<P>::r2()); }

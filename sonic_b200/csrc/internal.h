@@ -123,8 +123,9 @@ struct SrsRep {
 };
 
 // ---- srs.cu ------------------------------------------------------------------------------
-// Generates elements [first, first + count) of every level of the resident point array (the whole
-// array when count covers it); a multi-GPU runtime gives each device one slice and all-gathers.
+// Generates elements [first, first + count) of the resident point array taken as one flat array of
+// levels x 2(2d+1) points (the whole array when count covers it); a multi-GPU runtime gives each device one
+// equal slice and all-gathers once.
 // d_canon: x, alpha canonical (2 Fr) in device memory.  pre_c > 0 additionally fills levels
 // 1..W-1 with the 2^(pre_c j) multiples (W = ceil(255/pre_c)).
 // d_g2_points (nullable): also fills the G2 h-vectors, 2*(2d+1) affine G2 points, same exponent indexing, no hole.

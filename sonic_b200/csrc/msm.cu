@@ -299,10 +299,11 @@ static MsmPlan msm_plan(const Ctx& cx, uint32_t n_tot, int M, const MsmTables& t
     // whole number of waves (a proof sharded 8 ways has ~4 waves: a half-empty fifth cost 10 %)
     uint64_t entries = (uint64_t)n_tot * p.W;
     const uint64_t resident = (uint64_t)cx.sm_count * 512;
-    const uint64_t waves = std::max<uint64_t>(1, (entries + resident * 64 - 1) / (resident * 64));
+    const uint64_t Lmax = (uint64_t)(cx.opt_chunk_max > 0 ? cx.opt_chunk_max : 64);
+    const uint64_t waves = std::max<uint64_t>(1, (entries + resident * Lmax - 1) / (resident * Lmax));
     uint64_t L = (entries + resident * waves - 1) / (resident * waves);
     if (L < 8) L = 8;
-    if (L > 64) L = 64;
+    if (L > Lmax) L = Lmax;
     p.L = cx.opt_chunk > 0 ? (uint32_t)cx.opt_chunk : (uint32_t)L;
     return p;
 }

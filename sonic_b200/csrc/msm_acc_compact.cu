@@ -128,7 +128,19 @@ k_msm_accumulate_compact(const uint32_t* __restrict__ entries, const uint32_t* _
             else if (bend <= end) store_xyzz(buckets + gb, acc);
             else store_xyzz(tail + t, acc);
             if (p + 1 < end) {
-                do { ++gb; bend = offsets[gb + 1]; } while (bend <= p + 1);
+                ++gb;
+                bend = offsets[gb + 1];
+                if (bend <= p + 1) {
+                    // a run of empty buckets (a sliver of a job leaves most of its 2^(c-1) buckets empty: walking them
+                    // one load at a time cost a millisecond): last bucket whose offset is <= p + 1, by bisection
+                    uint32_t blo = gb, bhi = GB;
+                    while (bhi - blo > 1) {
+                        const uint32_t mid = (blo + bhi) >> 1;
+                        if (offsets[mid] <= p + 1) blo = mid; else bhi = mid;
+                    }
+                    gb = blo;
+                    bend = offsets[gb + 1];
+                }
                 cont = false;
                 fresh = true;
             }

@@ -60,6 +60,53 @@ k_msm_heavy(const uint32_t* __restrict__ offsets, uint32_t L, G1XYZZ* __restrict
     }
 }
 
+// Heavy buckets by quads, in two steps: (heavy bucket, part) work items -- HEAVY_SPLIT parts per bucket, each folded
+// by one block of 64 quads (pieces strided over the quads, tree through shared memory) -- and one quad per bucket to
+// fold the parts.  A 65 536-entry bucket (the all-ones weight rows of the synthetic circuits make dozens of them) has
+// ~1 300 pieces: one 128-thread block per bucket spent ~10 dependent additions per thread plus a 7-level tree
+// (0.25 ms of a rank's 8 ms at 8 GPUs); here the chain is 5 + 6 quad additions, then 4.
+constexpr int HQ_THREADS = 256;
+constexpr int HQ_QUADS = HQ_THREADS / 4;
+constexpr int HEAVY_SPLIT = 4;
+
+__global__ void __launch_bounds__(HQ_THREADS, 1)
+k_msm_heavy_quad(const uint32_t* __restrict__ offsets, uint32_t L, const G1XYZZ* __restrict__ head, const G1XYZZ* __restrict__ tail,
+                 const uint32_t* __restrict__ heavy_count, const uint32_t* __restrict__ heavy_list, G1XYZZ* __restrict__ parts) {
+    __shared__ G1XYZZ park[HQ_QUADS];
+    const Quad q;
+    const uint32_t qi = threadIdx.x >> 2;
+    const uint32_t items = *heavy_count * HEAVY_SPLIT;
+    for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+        const uint32_t gb = heavy_list[item / HEAVY_SPLIT], part = item % HEAVY_SPLIT;
+        const uint32_t a = offsets[gb], b = offsets[gb + 1];
+        const uint32_t t0 = a / L, t1 = (b - 1) / L;
+        G1XYZZ acc = G1XYZZ::inf();
+        for (uint32_t t = t0 + part * HQ_QUADS + qi; t <= t1; t += HQ_QUADS * HEAVY_SPLIT)
+            g1_add_quad(q, acc, load_xyzz(t == t0 ? tail + t0 : head + t));
+        if (q.lane == 0) park[qi] = acc;
+        __syncthreads();
+        for (uint32_t s = HQ_QUADS / 2; s > 0; s >>= 1) {
+            if (qi < s) g1_add_quad(q, acc, park[qi + s]);
+            __syncthreads();
+            if (qi < s && q.lane == 0) park[qi] = acc;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) store_xyzz(parts + item, acc);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_msm_heavy_fin(const uint32_t* __restrict__ heavy_count, const uint32_t* __restrict__ heavy_list, const G1XYZZ* __restrict__ parts,
+                G1XYZZ* __restrict__ buckets) {
+    const Quad q;
+    const uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    if (h >= *heavy_count) return;
+    G1XYZZ acc = load_xyzz(parts + (size_t)h * HEAVY_SPLIT);
+    for (int k = 1; k < HEAVY_SPLIT; ++k) g1_add_quad(q, acc, load_xyzz(parts + (size_t)h * HEAVY_SPLIT + k));
+    if (q.lane == 0) store_xyzz(buckets + heavy_list[h], acc);
+}
+
 // ---- stage 6: bucket reduction  sum_b (b+1) * B_b  per bucket set, level by level ----------------
 // Items come in sets of `count` consecutive elements; a thread folds K consecutive items of one
 // set with the running-sum trick (2 additions per item) and emits
@@ -283,10 +330,17 @@ void msm_reduce_stage(Ctx& cx, const MsmPlan& p, int M, const uint32_t* offsets,
     Arena& ar = cx.arena;
     cudaStream_t st = cx.stream;
     uint32_t* heavy_count = ar.get<uint32_t>(1);
-    uint32_t* heavy_list = ar.get<uint32_t>((size_t)chunks / MSM_HEAVY_PIECES + 2);
+    const size_t heavy_max = (size_t)chunks / MSM_HEAVY_PIECES + 2;
+    uint32_t* heavy_list = ar.get<uint32_t>(heavy_max);
     SONIC_CUDA(cudaMemsetAsync(heavy_count, 0, 4, st));
     SONIC_LAUNCH(k_msm_fixup, div_up(p.GB, 128), 128, 0, offsets, p.GB, p.L, buckets, head, tail, heavy_count, heavy_list);
-    SONIC_LAUNCH(k_msm_heavy, cx.sm_count * 2, MSM_RED_THREADS, 0, offsets, p.L, buckets, head, tail, heavy_count, heavy_list);
+    if (cx.opt_heavy_mode == 0) {
+        G1XYZZ* parts = ar.get<G1XYZZ>(heavy_max * HEAVY_SPLIT);
+        SONIC_LAUNCH(k_msm_heavy_quad, cx.sm_count, HQ_THREADS, 0, offsets, p.L, head, tail, heavy_count, heavy_list, parts);
+        SONIC_LAUNCH(k_msm_heavy_fin, div_up(heavy_max * 4, 128), 128, 0, heavy_count, heavy_list, parts, buckets);
+    } else {
+        SONIC_LAUNCH(k_msm_heavy, cx.sm_count * 2, MSM_RED_THREADS, 0, offsets, p.L, buckets, head, tail, heavy_count, heavy_list);
+    }
     SONIC_CUDA(cudaEventRecord(cx.ev[2], st));
 
     // Automatic (reduce_mode 0): quads while the stage is latency-bound -- few bucket sets: a standalone MSM, a small

@@ -690,12 +690,31 @@ int prove_enqueue(Ctx& cx, SrsRep& srs, const CircuitRep& circ_, const Fr* d_in,
         }
         const uint64_t total_len = pos[nshape];
         const uint32_t W_ = sharded ? world : 1;
+        // No slivers: a boundary that would leave only a few terms of an MSM on one side moves to that MSM's
+        // border.  A sliver costs its rank a whole bucket set (sort, reduction, finish) and the polynomial
+        // behind it for nothing -- 27 terms of one W'_j cost a rank 1.3 ms of 7.7 before this rule.
+        auto snap = [&](std::vector<uint64_t>& bd) {
+            const uint64_t floor_ = std::max<uint64_t>(4096, total_len / ((uint64_t)W_ * 64));
+            for (uint32_t r = 1; r < W_; ++r) {
+                const uint64_t b = bd[r];
+                for (uint32_t i = 0; i < nshape; ++i) {
+                    if (!(pos[i] < b && b < pos[i + 1])) continue;
+                    const uint64_t minp = std::min<uint64_t>((pos[i + 1] - pos[i]) / 2, floor_);
+                    if (b - pos[i] < minp) bd[r] = pos[i];
+                    else if (pos[i + 1] - b < minp) bd[r] = pos[i + 1];
+                    break;
+                }
+            }
+        };
         // run boundaries: equal runs first
         std::vector<uint64_t> bound(W_ + 1);
         for (uint32_t r = 0; r <= W_; ++r) bound[r] = total_len * r / W_;
-        // A rank that owns part of prT / prWt also builds t(X,y) (three NTTs), worth about 9n/8 terms
-        // of MSM work at n = 2^16: those ranks are dealt that much less, if the shorter runs leave the
-        // same ranks in charge of t (otherwise the equal runs stay).
+        snap(bound);
+        // A rank that owns part of prT / prWt also builds t(X,y) (three NTTs and a 7n-long opening).  With the
+        // Fr side built by ownership everywhere that is worth about n/2 terms of MSM work at n = 2^16 (measured
+        // per device at 8 GPUs: the t-owners hold fewer, longer MSMs and so also spend less in the bucket
+        // reduction): those ranks are dealt that much less, if the shorter runs leave the same ranks in charge
+        // of t (otherwise the equal runs stay).
         auto t_owners = [&](const std::vector<uint64_t>& bd) {
             std::vector<char> o(W_, 0);
             for (uint32_t r = 0; r < W_; ++r)
@@ -706,7 +725,7 @@ int prove_enqueue(Ctx& cx, SrsRep& srs, const CircuitRep& circ_, const Fr* d_in,
             return o;
         };
         if (sharded && has_main) {
-            const uint64_t V = (uint64_t)n + n / 8;
+            const uint64_t V = (uint64_t)n / 2;
             const std::vector<char> o1 = t_owners(bound);
             uint64_t k = 0;
             for (char c : o1) k += c;
@@ -718,7 +737,10 @@ int prove_enqueue(Ctx& cx, SrsRep& srs, const CircuitRep& circ_, const Fr* d_in,
                 if (o1[r] && cap < V) { ok = false; break; }
                 b2[r + 1] = b2[r] + cap - (o1[r] ? V : 0);
             }
-            if (ok && b2[W_] == total_len && t_owners(b2) == o1) bound = b2;
+            if (ok && b2[W_] == total_len) {
+                snap(b2);
+                if (t_owners(b2) == o1) bound = b2;
+            }
         }
         const uint64_t run_lo = sharded ? bound[rank] : 0, run_hi = sharded ? bound[rank + 1] : total_len;
         for (uint32_t i = 0; i < nshape; ++i) {

@@ -62,7 +62,7 @@ __global__ void k_selftest_g1_quad(int op, const G1XYZZ* __restrict__ a, const G
 
 // Latency probe: every thread runs a chain of `iters` DEPENDENT operations; with one warp per block and
 // one block per SM the time per operation is the latency a lone warp sees (the regime of the MSM's tail).
-//   0 fp_mul (Fq)   1 g1_add   2 g1_dbl   3 g1_madd   4 g1_add_quad   5 g1_dbl_quad
+//   0 fp_mul (Fq)   1 g1_add   2 g1_dbl   3 g1_madd   4 g1_add_quad   5 g1_dbl_quad   6 fp_mul_wide   7 fp_sqr   8 fp_mul_sub2
 __global__ void k_latency(int op, int iters, const G1XYZZ* __restrict__ seed, G1XYZZ* __restrict__ sink) {
     G1XYZZ acc = load_xyzz(seed), b = load_xyzz(seed + 1);
     G1Affine ba;
@@ -76,7 +76,10 @@ __global__ void k_latency(int op, int iters, const G1XYZZ* __restrict__ seed, G1
             case 2: acc = g1_dbl(acc); break;
             case 3: g1_madd(acc, ba); break;
             case 4: g1_add_quad(q, acc, b); break;
-            default: acc = g1_dbl_quad(q, acc); break;
+            case 5: acc = g1_dbl_quad(q, acc); break;
+            case 6: acc.x = fp_mul_wide(acc.x, b.x); break;
+            case 7: acc.x = fp_sqr(acc.x); break;
+            default: acc.x = fp_mul_sub2(acc.x, b.x, acc.x, b.y); break;
         }
     }
     if (threadIdx.x == 0) store_xyzz(sink + blockIdx.x, acc);

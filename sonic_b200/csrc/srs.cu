@@ -15,6 +15,8 @@
 // Device layout: one array of affine points indexed by exponent,
 //   points[family * (2d+1) + (k + d)],  k in [-d, d],  family 0 = plain, 1 = alpha;
 // the alpha slot k = 0 holds the infinity marker (0,0) and is never referenced by a job.
+#include <algorithm>
+
 #include "internal.h"
 #include "g1io.cuh"
 
@@ -156,20 +158,22 @@ static int srs_table_bits(uint64_t npoints) {
     return best;
 }
 
-// Generates elements [first, first + count) of every level of the resident point array (flat index
-// family * (2d+1) + k + d); the whole array when first = 0, count = 2*(2d+1).  A multi-GPU runtime
-// gives every device one slice and all-gathers the levels (capi.cu).  d_canon: x, alpha canonical
-// (2 Fr) in device memory.  Level 0 is the SRS itself; with pre_c > 0, level j holds the same points
-// times 2^(pre_c j), obtained from the same fixed-base table with the scalar multiplied by
-// 2^(pre_c j) mod r.  The scalars x^k, alpha x^k are cheap (two Fr products per element against
-// 16 x 3000 LMAC for the point) and are computed in full on every device.
+// Generates elements [first, first + count) of the resident point array taken as ONE flat array of
+// levels x npts points (flat index = level * npts + family * (2d+1) + k + d); everything when first = 0 and
+// count covers it.  A multi-GPU runtime gives every device one equal flat slice -- a slice may span two or
+// three levels -- and all-gathers once (capi.cu).  d_canon: x, alpha canonical (2 Fr) in device memory.
+// Level 0 is the SRS itself; with pre_c > 0, level j holds the same points times 2^(pre_c j), obtained from the
+// same fixed-base table with the scalar multiplied by 2^(pre_c j) mod r.  The scalars x^k, alpha x^k are
+// cheap (two Fr products per element against 16 x 3000 LMAC for the point) and are computed in full on
+// every device.
 void srs_generate(Ctx& cx, uint64_t d, const Fr* d_canon, G1Affine* d_points, int pre_c, uint64_t first, uint64_t count,
                   void* d_g2_points) {
     Arena& ar = cx.arena;
     const uint64_t stride = 2 * d + 1, npts = 2 * stride;
     const int levels = pre_c > 0 ? (255 + pre_c - 1) / pre_c : 1;
-    if (first > npts) first = npts;
-    if (count > npts - first) count = npts - first;
+    const uint64_t total = npts * (uint64_t)levels;
+    if (first > total) first = total;
+    if (count > total - first) count = total - first;
     Fr* mont = ar.get<Fr>(3);
     SONIC_LAUNCH(k_srs_params, 1, 32, 0, d_canon, mont);
     Fr* scal_m = ar.get<Fr>(npts);
@@ -177,7 +181,7 @@ void srs_generate(Ctx& cx, uint64_t d, const Fr* d_canon, G1Affine* d_points, in
     if (count) {
         Fr* consts = ar.get<Fr>(levels);
         SONIC_LAUNCH(k_level_consts, div_up(levels, 32), 32, 0, pre_c > 0 ? pre_c : 1, levels, consts);
-        const int w = srs_table_bits(count * (uint64_t)levels);
+        const int w = srs_table_bits(count);
         const int Wt = (255 + w - 1) / w;
         const size_t tsize = (size_t)Wt << w;
         G1XYZZ* Tx = ar.get<G1XYZZ>(tsize);
@@ -186,15 +190,19 @@ void srs_generate(Ctx& cx, uint64_t d, const Fr* d_canon, G1Affine* d_points, in
         for (int l = 1; l < w; ++l)
             SONIC_LAUNCH(k_tbl_level, dim3(div_up(1u << l, 128), (unsigned)Wt), 128, 0, Tx, w, Wt, l);
         SONIC_LAUNCH(k_batch_affine, div_up(div_up(tsize, AFF_BATCH), 128), 128, 0, Tx, Ta, (uint64_t)tsize);
-        Fr* scal = ar.get<Fr>(count);
-        G1XYZZ* px = ar.get<G1XYZZ>(count);
-        // alpha family, exponent 0: g^alpha is not part of the SRS
-        const uint64_t hole_abs = stride + d;
-        const uint64_t hole = hole_abs >= first && hole_abs < first + count ? hole_abs - first : ~0ull;
+        const uint64_t piece_max = std::min<uint64_t>(count, npts);
+        Fr* scal = ar.get<Fr>(piece_max);
+        G1XYZZ* px = ar.get<G1XYZZ>(piece_max);
+        const uint64_t hole_abs = stride + d;   // alpha family, exponent 0: g^alpha is not part of the SRS
         for (int j = 0; j < levels; ++j) {
-            SONIC_LAUNCH(k_level_scalars, div_up(count, 256), 256, 0, scal_m + first, consts + j, count, scal);
-            SONIC_LAUNCH(k_fixed_base, div_up(count, 128), 128, 0, scal, Ta, w, Wt, count, hole, px);
-            SONIC_LAUNCH(k_batch_affine, div_up(div_up(count, AFF_BATCH), 128), 128, 0, px, d_points + (size_t)j * npts + first, count);
+            // the part of level j inside the flat slice
+            const uint64_t lo = std::max<uint64_t>(first, (uint64_t)j * npts), hi = std::min<uint64_t>(first + count, (uint64_t)(j + 1) * npts);
+            if (hi <= lo) continue;
+            const uint64_t a = lo - (uint64_t)j * npts, n = hi - lo;
+            const uint64_t hole = hole_abs >= a && hole_abs < a + n ? hole_abs - a : ~0ull;
+            SONIC_LAUNCH(k_level_scalars, div_up(n, 256), 256, 0, scal_m + a, consts + j, n, scal);
+            SONIC_LAUNCH(k_fixed_base, div_up(n, 128), 128, 0, scal, Ta, w, Wt, n, hole, px);
+            SONIC_LAUNCH(k_batch_affine, div_up(div_up(n, AFF_BATCH), 128), 128, 0, px, d_points + lo, n);
         }
     }
     if (d_g2_points) srs_generate_g2(cx, scal_m, npts, d_g2_points);

@@ -26,9 +26,10 @@ def deal_terms(lengths: Sequence[int], world: int, t_msms: Sequence[int] = (), t
     """How prove_run (csrc/prove.cu) shards one proof: the (clipped) exponent windows of all MSMs,
     concatenated in record order, are cut into `world` runs of terms.  Returns, per rank, the
     part [a, b) of every MSM's window (offsets into the window; a == b where the rank holds nothing).
-    A rank owns a few whole MSMs and at most two partial ones; at most world-1 MSMs are split.
+    A rank owns a few whole MSMs and at most two partial ones; at most world-1 MSMs are split; a boundary
+    never leaves a sliver of an MSM (fewer than min(len/2, max(4096, total/(64 world))) terms) on either side.
     The runs are equal, except that ranks owning part of the MSMs `t_msms` (prT and prWt, records 1
-    and 4 of `prove`: those ranks also build t(X,y)) are dealt `t_extra` (= n + n/8) terms less when
+    and 4 of `prove`: those ranks also build t(X,y)) are dealt `t_extra` (= n/2) terms less when
     that leaves the same ranks in charge of them."""
     total = sum(lengths)
     pos = [0]
@@ -38,7 +39,22 @@ def deal_terms(lengths: Sequence[int], world: int, t_msms: Sequence[int] = (), t
     def owners(bd):
         return [any(min(bd[r + 1], pos[i + 1]) > max(bd[r], pos[i]) for i in t_msms) for r in range(world)]
 
-    bound = [total * r // world for r in range(world + 1)]
+    def snap(bd):
+        """No slivers: a boundary that would leave only a few terms of an MSM on one side moves to that MSM's border."""
+        floor_ = max(4096, total // (world * 64))
+        for r in range(1, world):
+            b = bd[r]
+            for i, n in enumerate(lengths):
+                if pos[i] < b < pos[i + 1]:
+                    minp = min(n // 2, floor_)
+                    if b - pos[i] < minp:
+                        bd[r] = pos[i]
+                    elif pos[i + 1] - b < minp:
+                        bd[r] = pos[i + 1]
+                    break
+        return bd
+
+    bound = snap([total * r // world for r in range(world + 1)])
     if t_msms and t_extra > 0:
         o1 = owners(bound)
         k = sum(o1)
@@ -52,7 +68,7 @@ def deal_terms(lengths: Sequence[int], world: int, t_msms: Sequence[int] = (), t
                 ok = False
                 break
             b2.append(b2[-1] + cap - (t_extra if o1[r] else 0))
-        if ok and b2[-1] == total and owners(b2) == o1:
+        if ok and b2[-1] == total and owners(snap(b2)) == o1:
             bound = b2
     out = []
     for rank in range(world):
