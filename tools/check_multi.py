@@ -38,4 +38,26 @@ say("oracle ok")
 assert sb.prove_bytes(g, ga, gc, rnd) == want
 say("prove ok")
 assert sb.prove_batch(g, [ga] * 5, gc, [rnd] * 5) == [want] * 5
+# persistence with several devices: the file is read once and uploaded to every device
+import tempfile
+with tempfile.TemporaryDirectory() as tmp:
+    path = os.path.join(tmp, "srs.bin")
+    g.save(path)
+    g2 = sb.SRS.load(path)
+    assert g2.srsD == d and g2.gNegativeX == g.gNegativeX
+    assert sb.prove_bytes(g2, ga, gc, rnd) == want
+say("save/load ok")
+# a standalone MSM cut across the devices, and an unsatisfied assignment: the same panic as on one device
+sb.set_option("shard_min_terms", 8)
+sc = [rng.randrange(R) for _ in range(2 * d + 1)]
+xi = pow(x, -1, R)
+acc = sum(v * (pow(x, k - d, R) if k >= d else pow(xi, d - k, R)) for k, v in enumerate(sc)) % R
+assert sb.msm(g, 0, -d, sc) == bls.g1_compress(bls.g1_mul_gen(acc))
+bad = sb.Assignment(list(assignment.aL), list(assignment.aR), [(assignment.aO[0] + 1) % R] + list(assignment.aO[1:]))
+try:
+    sb.prove_bytes(g, bad, gc, rnd)
+    raise SystemExit("an unsatisfied assignment produced a proof")
+except sb.SonicError as e:
+    assert e.text == "commitPoly: gNegativeAlphaX is not long enough: -1 >= %d" % d, e.text
+say("msm + panic ok")
 print("ok", ndev, flush=True)
