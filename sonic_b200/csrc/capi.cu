@@ -551,8 +551,11 @@ void shutdown_locked() {
         cx.pinned = nullptr;
         cx.pinned_cap = 0;
         for (auto& e : cx.ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+        for (auto& e : cx.ovl) { if (e) cudaEventDestroy(e); e = nullptr; }
         cudaStreamDestroy(cx.stream);
         cx.stream = nullptr;
+        if (cx.stream2) cudaStreamDestroy(cx.stream2);
+        cx.stream2 = nullptr;
         cx.ready = false;
     }
     cudaSetDevice(ctx_slots()[0].device);
@@ -599,8 +602,14 @@ int sonic_init(const int* devices, int ndev) {
             cx.device = devs[r];
             cx.slot = r;
             cx.sm_count = prop.multiProcessorCount;
-            SONIC_CUDA(cudaStreamCreateWithFlags(&cx.stream, cudaStreamNonBlocking));
+            // the main stream carries the latency-bound tails and gets the higher priority; the second stream only ever
+            // runs the second half of a proof's MSMs under the first half's tail
+            int prio_least = 0, prio_greatest = 0;
+            SONIC_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+            SONIC_CUDA(cudaStreamCreateWithPriority(&cx.stream, cudaStreamNonBlocking, prio_greatest));
+            SONIC_CUDA(cudaStreamCreateWithPriority(&cx.stream2, cudaStreamNonBlocking, prio_least));
             for (auto& e : cx.ev) SONIC_CUDA(cudaEventCreate(&e));
+            for (auto& e : cx.ovl) SONIC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             cx.launches = 0;
             cx.ready = true;
         }
@@ -1579,6 +1588,9 @@ int sonic_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "chunk")) {
         if (value < 0 || value > 4096) return fail(SONIC_ERR_INVALID_ARG, "chunk must be in [0, 4096]");
         each([&](Ctx& cx) { cx.opt_chunk = (int)value; });
+    } else if (!strcmp(name, "overlap")) {
+        if (value < 0 || value > 1) return fail(SONIC_ERR_INVALID_ARG, "overlap must be 0 or 1");
+        each([&](Ctx& cx) { cx.opt_overlap = (int)value; });
     } else if (!strcmp(name, "heavy_mode")) {
         if (value < 0 || value > 1) return fail(SONIC_ERR_INVALID_ARG, "heavy_mode must be 0 or 1");
         each([&](Ctx& cx) { cx.opt_heavy_mode = (int)value; });

@@ -111,12 +111,15 @@ struct Ctx {
     int slot = 0;                                         // position in the sonic_init device list (= rank of in-library sharding)
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;   // second half of a proof's MSMs (its sort and accumulation overlap the first half's latency-bound tail)
+    cudaEvent_t ovl[4] = {};          // fork / accumulate-done / join events of that overlap
     Arena arena;
     std::mutex mu;  // calls may arrive from several OS threads (package.yaml:98-101: -threaded)
     uint64_t launches = 0;
     int opt_window_bits = 0;
     int opt_chunk = 0;
     int opt_heavy_mode = 0;                               // 0 heavy buckets by quads in two steps, 1 one 128-thread block per heavy bucket
+    int opt_overlap = 0;                                  // 1: two MSM batches per proof on two streams (tail of the first under the accumulation of the second); measured slower, off
     int opt_chunk_max = 0;                                // longest chunk the automatic rule may pick (0 = default)
     int opt_acc_mode = 1;                                 // 0 straight-line mixed addition in registers, 1 compact (operand file in shared memory)
     bool opt_g2 = false;                                  // SRS.new also generates the G2 h-vectors
@@ -130,7 +133,9 @@ struct Ctx {
     std::map<std::string, double> timing_ms;
     std::map<uint32_t, void*> ntt_cache;  // log2(length) -> resident twiddle tables
     const uint32_t* msm_offsets_total = nullptr;  // device address of the last batch's entry count
-    cudaEvent_t ev[16] = {};  // 0-3,8,9 msm stages; 4,5 poly / microbench; 6,7 call timer; 10-15 bench marks
+    const uint32_t* msm_offsets_total2 = nullptr; // the same for the second half of an overlapped pair
+    bool msm_second_half = false;                 // the last MSM ran as two overlapped halves
+    cudaEvent_t ev[24] = {};  // 0-3,8,9 msm stages; 4,5 poly / microbench; 6,7 call timer; 10-15 bench marks; 16-21 msm stages of the second half (overlap)
     char* pinned = nullptr;  // staging for small D2H results
     size_t pinned_cap = 0;
 };

@@ -36,8 +36,15 @@ struct MsmTables {
     int W = 0;
     uint32_t stride = 0;
 };
+// `sync` (optional) orders two batches that run on two streams: the bucket accumulation -- the one stage that
+// fills the machine -- waits for `wait_before_acc` and signals `signal_after_acc`.
+struct MsmSync {
+    cudaEvent_t wait_before_acc = nullptr;
+    cudaEvent_t signal_after_acc = nullptr;
+    bool second = false;   // the second half: its stage events and counters go to their own slots
+};
 void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const uint32_t* d_scalars,
-             const std::vector<MsmJob>& jobs, G1Affine* d_out_aff, uint8_t* d_out_comp);
+             const std::vector<MsmJob>& jobs, G1Affine* d_out_aff, uint8_t* d_out_comp, const MsmSync* sync = nullptr);
 void msm_collect_timing(Ctx& cx);
 void exclusive_scan_u32(Arena& ar, const uint32_t* in, uint32_t* out, uint32_t n);
 

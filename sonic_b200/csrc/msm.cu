@@ -311,7 +311,15 @@ static MsmPlan msm_plan(const Ctx& cx, uint32_t n_tot, int M, const MsmTables& t
 // d_scalars: canonical little-endian scalars, 8 words each.  Results: one affine point
 // (Montgomery form) and/or one 48-byte compressed encoding per job, in device memory.
 void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const uint32_t* d_scalars,
-             const std::vector<MsmJob>& jobs, G1Affine* d_out_aff, uint8_t* d_out_comp) {
+             const std::vector<MsmJob>& jobs, G1Affine* d_out_aff, uint8_t* d_out_comp, const MsmSync* sync) {
+    const bool second = sync && sync->second;
+    // stage events: 0 sort begins, 1 sort done, 2 fix-up done, 3 finish done, 4 / 5 around the accumulate kernel
+    cudaEvent_t* E = second ? &cx.ev[16] : nullptr;
+    auto mark = [&](int k) {
+        static const int first_half[6] = {0, 1, 2, 3, 8, 9};
+        SONIC_CUDA(cudaEventRecord(second ? E[k] : cx.ev[first_half[k]], cx.stream));
+    };
+    if (!second) cx.msm_second_half = false;
     const int M = (int)jobs.size();
     if (M == 0) return;
     if (M > MSM_MAX_JOBS) throw CudaError{cudaErrorInvalidValue, "too many MSM jobs", __LINE__};
@@ -333,7 +341,7 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const u
     if ((uint64_t)n_tot * p.W >= (1ull << 32)) throw CudaError{cudaErrorInvalidValue, "MSM batch too large", __LINE__};
     cudaStream_t st = cx.stream;
 
-    SONIC_CUDA(cudaEventRecord(cx.ev[0], st));
+    mark(0);
     uint32_t* offsets = ar.get<uint32_t>((size_t)p.GB + 1);
     // zero digits are not stored, so n_tot*W is only an upper bound of the entry count; the
     // accumulate grid is sized for the bound and reads the true count from offsets[GB]
@@ -354,7 +362,7 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const u
     const uint64_t hist_len = (uint64_t)tiles * p.sets * p.B;
     const size_t sort_smem = (size_t)p.B * sizeof(uint32_t);
     const bool tiled = cx.opt_sort_mode != 0 && n_tot > 0 && sort_smem <= (size_t(128) << 10) && hist_len <= (1ull << 26);  // <= 256 MB of histograms
-    cx.timing_ms["msm.sort_tiles"] = tiled ? tiles : 0;
+    if (!second) cx.timing_ms["msm.sort_tiles"] = tiled ? tiles : 0;
     if (tiled) {
         if (sort_smem > (size_t(48) << 10)) {  // opt-in above 48 KB; a host-side attribute, set per launch so that it follows the device
             SONIC_CUDA(cudaFuncSetAttribute(k_msm_sort_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10));
@@ -374,45 +382,70 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const u
         SONIC_CUDA(cudaMemcpyAsync(cursors, offsets, ((size_t)p.GB + 1) * 4, cudaMemcpyDeviceToDevice, st));
         if (n_tot) SONIC_LAUNCH(k_msm_digits<true>, div_up(n_tot, 256), 256, 0, d_scalars, tab, n_tot, p.c, p.W, p.B, level_stride, cursors, entries);
     }
-    SONIC_CUDA(cudaEventRecord(cx.ev[1], st));
+    mark(1);
 
     const uint32_t chunks = div_up(total_max, p.L);
     G1XYZZ* buckets = ar.get<G1XYZZ>(p.GB);
     G1XYZZ* head = ar.get<G1XYZZ>(chunks ? chunks : 1);
     G1XYZZ* tail = ar.get<G1XYZZ>(chunks ? chunks : 1);
-    SONIC_CUDA(cudaEventRecord(cx.ev[8], st));
+    if (sync && sync->wait_before_acc) SONIC_CUDA(cudaStreamWaitEvent(st, sync->wait_before_acc, 0));
+    mark(4);
     if (chunks) {
         if (cx.opt_acc_mode == 1) launch_accumulate_compact(cx, chunks, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
         else launch_accumulate_regs(cx, chunks, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
     }
-    SONIC_CUDA(cudaEventRecord(cx.ev[9], st));
-    cx.timing_ms["msm.window_bits"] = p.c;
-    cx.timing_ms["msm.windows"] = p.W;
-    cx.timing_ms["msm.precomputed"] = tables.c > 0 ? 1 : 0;
-    cx.timing_ms["msm.terms"] = n_tot;
-    cx.timing_ms["msm.jobs"] = M;
-    cx.timing_ms["msm.chunk"] = p.L;
-    cx.timing_ms["msm.buckets"] = p.GB;
-    cx.msm_offsets_total = offsets + p.GB;
-    msm_reduce_stage(cx, p, M, offsets, chunks, buckets, head, tail, d_out_aff, d_out_comp);
-    SONIC_CUDA(cudaEventRecord(cx.ev[3], st));
+    mark(5);
+    if (sync && sync->signal_after_acc) SONIC_CUDA(cudaEventRecord(sync->signal_after_acc, st));
+    if (!second) {
+        cx.timing_ms["msm.window_bits"] = p.c;
+        cx.timing_ms["msm.windows"] = p.W;
+        cx.timing_ms["msm.precomputed"] = tables.c > 0 ? 1 : 0;
+        cx.timing_ms["msm.terms"] = n_tot;
+        cx.timing_ms["msm.jobs"] = M;
+        cx.timing_ms["msm.chunk"] = p.L;
+        cx.timing_ms["msm.buckets"] = p.GB;
+        cx.msm_offsets_total = offsets + p.GB;
+    } else {
+        cx.timing_ms["msm.terms"] += n_tot;
+        cx.timing_ms["msm.jobs"] += M;
+        cx.timing_ms["msm.buckets"] += p.GB;
+        cx.msm_offsets_total2 = offsets + p.GB;
+        cx.msm_second_half = true;
+    }
+    msm_reduce_stage(cx, p, M, offsets, chunks, buckets, head, tail, d_out_aff, d_out_comp, second ? E[2] : cx.ev[2]);
+    mark(3);
 }
 
+// Stage times of the last batch.  When it ran as two overlapped halves (prove.cu) the stages are those of the pair:
+// sort = the first half's (the second's is hidden), accumulate = first sort done -> second fix-up done, reduce = the
+// second half's exposed tail, accumulate_kernel / entries / terms = both halves together.
 void msm_collect_timing(Ctx& cx) {
+    const bool two = cx.msm_second_half;
+    cudaEvent_t* E = &cx.ev[16];
     float a = 0, b = 0, c = 0;
     if (cudaEventElapsedTime(&a, cx.ev[0], cx.ev[1]) == cudaSuccess &&
-        cudaEventElapsedTime(&b, cx.ev[1], cx.ev[2]) == cudaSuccess &&
-        cudaEventElapsedTime(&c, cx.ev[2], cx.ev[3]) == cudaSuccess) {
+        cudaEventElapsedTime(&b, cx.ev[1], two ? E[2] : cx.ev[2]) == cudaSuccess &&
+        cudaEventElapsedTime(&c, two ? E[2] : cx.ev[2], two ? E[3] : cx.ev[3]) == cudaSuccess) {
         cx.timing_ms["msm.sort"] = a;
         cx.timing_ms["msm.accumulate"] = b;
         cx.timing_ms["msm.reduce"] = c;
         cx.timing_ms["msm"] = a + b + c;
     }
-    float k = 0;
-    if (cudaEventElapsedTime(&k, cx.ev[8], cx.ev[9]) == cudaSuccess) cx.timing_ms["msm.accumulate_kernel"] = k;
+    float k = 0, k2 = 0;
+    if (cudaEventElapsedTime(&k, cx.ev[8], cx.ev[9]) == cudaSuccess) {
+        if (two && cudaEventElapsedTime(&k2, E[4], E[5]) == cudaSuccess) k += k2;
+        cx.timing_ms["msm.accumulate_kernel"] = k;
+    }
+    if (two) {
+        float t1 = 0;
+        if (cudaEventElapsedTime(&t1, cx.ev[2], cx.ev[3]) == cudaSuccess) cx.timing_ms["msm.reduce_hidden"] = t1;   // the first half's tail, under the second's accumulation
+    }
     if (cx.msm_offsets_total) {
-        uint32_t total = 0;
-        if (cudaMemcpy(&total, cx.msm_offsets_total, 4, cudaMemcpyDeviceToHost) == cudaSuccess) cx.timing_ms["msm.entries"] = total;
+        uint32_t total = 0, total2 = 0;
+        if (cudaMemcpy(&total, cx.msm_offsets_total, 4, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            if (two && cx.msm_offsets_total2) cudaMemcpy(&total2, cx.msm_offsets_total2, 4, cudaMemcpyDeviceToHost);
+            cx.timing_ms["msm.entries"] = (double)total + (double)total2;
+        }
     }
 }
 

@@ -26,6 +26,6 @@ void launch_accumulate_compact(Ctx& cx, uint32_t chunks, const uint32_t* entries
 
 // stages 5-7 (msm_reduce.cu)
 void msm_reduce_stage(Ctx& cx, const MsmPlan& p, int M, const uint32_t* offsets, uint32_t chunks, G1XYZZ* buckets,
-                      const G1XYZZ* head, const G1XYZZ* tail, G1Affine* d_out_aff, uint8_t* d_out_comp);
+                      const G1XYZZ* head, const G1XYZZ* tail, G1Affine* d_out_aff, uint8_t* d_out_comp, cudaEvent_t fixup_done);
 
 }  // namespace sonic

@@ -326,7 +326,7 @@ k_msm_finish(const G1XYZZ* __restrict__ partial, uint32_t S, int W, int c, G1Aff
 
 // ---- host side ---------------------------------------------------------------------------
 void msm_reduce_stage(Ctx& cx, const MsmPlan& p, int M, const uint32_t* offsets, uint32_t chunks, G1XYZZ* buckets,
-                      const G1XYZZ* head, const G1XYZZ* tail, G1Affine* d_out_aff, uint8_t* d_out_comp) {
+                      const G1XYZZ* head, const G1XYZZ* tail, G1Affine* d_out_aff, uint8_t* d_out_comp, cudaEvent_t fixup_done) {
     Arena& ar = cx.arena;
     cudaStream_t st = cx.stream;
     uint32_t* heavy_count = ar.get<uint32_t>(1);
@@ -341,7 +341,7 @@ void msm_reduce_stage(Ctx& cx, const MsmPlan& p, int M, const uint32_t* offsets,
     } else {
         SONIC_LAUNCH(k_msm_heavy, cx.sm_count * 2, MSM_RED_THREADS, 0, offsets, p.L, buckets, head, tail, heavy_count, heavy_list);
     }
-    SONIC_CUDA(cudaEventRecord(cx.ev[2], st));
+    SONIC_CUDA(cudaEventRecord(fixup_done, st));
 
     // Automatic (reduce_mode 0): quads while the stage is latency-bound -- few bucket sets: a standalone MSM, a small
     // proof, one rank's share of a sharded proof (one job of 2^15 buckets: 0.97 -> 0.55 ms; prove at n = 2^13: 1.33 -> 0.95) --
