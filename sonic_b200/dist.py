@@ -77,6 +77,22 @@ def deal_terms(lengths: Sequence[int], world: int, t_msms: Sequence[int] = (), t
     return out
 
 
+def value_leads(deal: List[List[Tuple[int, int]]], Q: int) -> List[int]:
+    """Which rank contributes each device-computed field value of a sharded proof (mirror of prove.cu): the lowest
+    rank holding terms of the MSM the value's opening belongs to (rank 0 for an empty window).  Values in record
+    order: prA (opening prWa, record 2), prB (prWb, 3), prS (led by prT's first rank, 1), s_j (W_j), s'_j (Q_j).
+    Every other rank leaves zeros in its exchange record and the fold ORs the bytes."""
+    def first(i):
+        for r, parts in enumerate(deal):
+            if parts[i][1] > parts[i][0]:
+                return r
+        return 0
+
+    base = 5
+    msm_of = [2, 3, 1] + [base + 2 * j + 1 for j in range(Q)] + [base + 2 * Q + 2 * j + 1 for j in range(Q)]
+    return [first(i) for i in msm_of]
+
+
 def all_gather_bytes(blob: bytes, group=None) -> List[bytes]:
     """All-gather of one fixed-size byte blob per rank; returns the blobs in rank order."""
     world = dist.get_world_size(group)

@@ -43,10 +43,16 @@ def _worker(rank, world, port, result_dir):
     # this rank's shard blob: raw partial sums over its slice of every MSM, then the Fr values
     parts = []
     windows = [(max(lo, -d), min(lo + len(scal), d + 1)) for _, lo, scal in msms]
-    mine = sdist.deal_terms([chi - clo for clo, chi in windows], world, t_msms=(1, 4), t_extra=12 // 2)[rank]
+    deal = sdist.deal_terms([chi - clo for clo, chi in windows], world, t_msms=(1, 4), t_extra=12 // 2)
+    mine = deal[rank]
     for (alpha, lo, scal), (clo, chi), (a, b) in zip(msms, windows, mine):
         parts.append(bls.g1_to_raw(S.fold_msm(srs, (alpha, lo, scal), clo + a, clo + b)))
-    blob = b"".join(parts) + b"".join(bls.fr_to_bytes(v) for v in fvals)
+    # the exchange record of this rank (include/sonic_b200.h: sonic_prove_shard): raw partial sums, then the field values
+    # this rank LEADS (zeros elsewhere), then hscU, hscV which every rank knows
+    leads = sdist.value_leads(deal, Q)
+    nv = 2 * Q + 3
+    vals = [bls.fr_to_bytes(v) if leads[k] == rank else bytes(32) for k, v in enumerate(fvals[:nv])]
+    blob = b"".join(parts) + b"".join(vals) + b"".join(bls.fr_to_bytes(v) for v in fvals[nv:])
     blobs = sdist.all_gather_bytes(blob)
     assert len(blobs) == world and blobs[rank] == blob
     nm = len(msms)
@@ -56,7 +62,17 @@ def _worker(rank, world, port, result_dir):
         for r in range(world):
             acc = bls.g1_add(acc, bls.g1_from_raw(blobs[r][96 * m:96 * m + 96]))
         g48.append(bls.g1_compress(acc))
-    fv = [bls.fr_from_bytes(blobs[0][96 * nm + 32 * i:96 * nm + 32 * i + 32]) for i in range(len(fvals))]
+    # fold of the values: exactly one rank contributed each, so the bytes are OR-ed
+    fv = []
+    for i in range(len(fvals)):
+        if i < nv:
+            word = 0
+            for r in range(world):
+                word |= int.from_bytes(blobs[r][96 * nm + 32 * i:96 * nm + 32 * i + 32], "little")
+            fv.append(word)
+        else:
+            fv.append(bls.fr_from_bytes(blobs[rank][96 * nm + 32 * i:96 * nm + 32 * i + 32]))
+    assert sorted(set(leads)) == sorted(set(leads) & set(range(world))) and len(leads) == nv
     proof = S.assemble_proof_bytes(Q, g48, fv)
     want, _ = S.prove_dense(srs, assignment, circuit, rnd)
     ok = proof == S.encode_proof(want)

@@ -245,3 +245,60 @@ def test_window_tables_restricted_to_the_circuit_size(gpu):
     want = cref.prove(table, d, n, Q, c["wL"], c["wR"], c["wO"], c["cs"], c["aL"], c["aR"], c["aO"],
                       np.frombuffer(synth.ints_to_bytes(rnd), dtype=np.uint8).copy(), threads=8)
     assert full[0] == want
+
+
+def test_far_exponents_and_damaged_srs_files(gpu, tmp_path):
+    """a short polynomial at a far exponent must give the reference's `index` panic from host-side bounds
+    (not an out-of-memory error, not a truncated window); an SRS file whose header breaks the invariants SRS.new
+    enforces, or whose size disagrees with its header, is refused."""
+    import struct
+
+    from sonic_b200 import capi
+
+    rng = random.Random(61)
+    d = 20
+    x, alpha = rng.randrange(1, R), rng.randrange(1, R)
+    g, o = gpu.SRS.new(d, x, alpha), S.srs_new(d, x, alpha)
+    for e in (10 ** 9, -10 ** 9, 2 ** 40, -2 ** 40, 2 ** 62):
+        f = {e: 5}
+        with pytest.raises(gpu.SonicError) as ge:
+            gpu.commitPoly(g, d, f)
+        assert ge.value.kind == "SRS_TOO_SHORT"
+        if abs(e) <= 10 ** 9:
+            with pytest.raises(S.SonicPanic) as oe:
+                S.commitPoly(o, d, f)
+            assert ge.value.text == str(oe.value)
+        with pytest.raises(gpu.SonicError) as ge:
+            gpu.openPoly(g, 7, f)
+        assert ge.value.kind == "SRS_TOO_SHORT" and "is not long enough" in ge.value.text
+    # zero coefficients far away are not terms: the polynomial below is 3 X^2
+    f = {2: 3, 10 ** 12: 0, -10 ** 12: 0}
+    assert gpu.commitPoly(g, d, f) == C(S.commitPoly(o, d, {2: 3}))
+    v, w = gpu.openPoly(g, 9, f)
+    vo, wo = S.openPoly(o, 9, {2: 3})
+    assert (v, w) == (vo, C(wo))
+    # z = 0 with a negative power: recip 0, whatever zeros pad the window
+    with pytest.raises(gpu.SonicError) as ge:
+        gpu.openPoly(g, 0, {-1: 1, 3: 2})
+    assert ge.value.kind == "DIV_BY_ZERO"
+    # SRS files
+    path = str(tmp_path / "srs.bin")
+    g.save(path)
+    blob = open(path, "rb").read()
+    assert gpu.SRS.load(path).gPositiveX == g.gPositiveX
+    magic, version, pre_c, dd, levels, ppl = struct.unpack_from("<8sIIQQQ", blob)
+    assert magic == b"SONICSRS" and dd == d and ppl == 2 * (2 * d + 1)
+
+    def refused(data):
+        bad = str(tmp_path / "bad.bin")
+        open(bad, "wb").write(data)
+        with pytest.raises(gpu.SonicError) as e:
+            gpu.SRS.load(bad)
+        assert e.value.kind == "INVALID_ARG"
+
+    refused(blob[:-1])                                                              # truncated
+    refused(blob + b"\0")                                                           # longer than its header says
+    refused(blob[:20])                                                              # shorter than the header
+    refused(struct.pack("<8sIIQQQ", magic, version, 255, dd, 1, ppl) + blob[40:])   # window bits out of range
+    refused(struct.pack("<8sIIQQQ", magic, version, pre_c, dd, levels + 1, ppl) + blob[40:])
+    refused(struct.pack("<8sIIQQQ", b"NOTANSRS", version, pre_c, dd, levels, ppl) + blob[40:])
