@@ -60,11 +60,13 @@ k_msm_heavy(const uint32_t* __restrict__ offsets, uint32_t L, G1XYZZ* __restrict
     }
 }
 
-// Heavy buckets by quads, in two steps: (heavy bucket, part) work items -- HEAVY_SPLIT parts per bucket, each folded
-// by one block of 64 quads (pieces strided over the quads, tree through shared memory) -- and one quad per bucket to
-// fold the parts.  A 65 536-entry bucket (the all-ones weight rows of the synthetic circuits make dozens of them) has
-// ~1 300 pieces: one 128-thread block per bucket spent ~10 dependent additions per thread plus a 7-level tree
-// (0.25 ms of a rank's 8 ms at 8 GPUs); here the chain is 5 + 6 quad additions, then 4.
+// Heavy buckets by quads, in two steps (option heavy_mode = 0; NOT the default): (heavy bucket, part) work items --
+// HEAVY_SPLIT parts per bucket, each folded by one block of 64 quads (pieces strided over the quads, tree through
+// shared memory) -- and one quad per bucket to fold the parts.  A 65 536-entry bucket (the all-ones weight rows of the
+// synthetic circuits make dozens of them) has ~1 000 pieces.  Measured against one 128-thread block per bucket
+// (k_msm_heavy): nothing at 8 GPUs (0.25 ms per rank either way: two rounds of items per SM), slower on one GPU
+// (400 heavy buckets: 0.27 -> 0.47 ms, profiles/r02h_others_ncu.md): at 190 registers only 8 warps fit an SM and a
+// quad spends four lanes per addition, so with many buckets the plain kernel's thread-level parallelism wins.
 constexpr int HQ_THREADS = 256;
 constexpr int HQ_QUADS = HQ_THREADS / 4;
 constexpr int HEAVY_SPLIT = 4;
