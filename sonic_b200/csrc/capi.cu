@@ -647,6 +647,24 @@ int sonic_init(const int* devices, int ndev) {
         }
         SONIC_CUDA(cudaSetDevice(devs[0]));
         ctx_bind(&ctx_slots()[0]);
+        if (ndev > 1) {
+            // NCCL connects its channels lazily, at the first collective (~0.3 s on 8 GPUs): pay that here, not inside
+            // the first SRS.new or prove
+            int rc = on_all_locked([&](int r, Ctx& cx) -> int {
+                return attempt(cx, [&]() -> int {
+                    uint8_t* buf = cx.arena.get<uint8_t>(256 * (size_t)(ndev + 1));
+                    SONIC_CUDA(cudaMemsetAsync(buf, 0, 256 * (size_t)(ndev + 1), cx.stream));
+                    SONIC_NCCL(ncclAllGather(buf + 256 * (size_t)ndev, buf, 256, ncclUint8, R.comm[r], cx.stream));
+                    SONIC_CUDA(cudaStreamSynchronize(cx.stream));
+                    return (int)SONIC_OK;
+                });
+            });
+            if (rc != SONIC_OK) {
+                const std::string why = last_error_text();
+                shutdown_locked();
+                return fail(rc, "NCCL warm-up over %d devices failed: %s", ndev, why.c_str());
+            }
+        }
         // a process that exits without sonic_shutdown must not hang in the teardown of live NCCL communicators and
         // worker threads: registered after the CUDA runtime came up, so it runs before the runtime's own exit handler
         static bool at_exit_registered = false;
