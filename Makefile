@@ -2,7 +2,7 @@
 NVCC ?= nvcc
 NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v $(EXTRA)
 CSRC := sonic_b200/csrc
-OBJS := $(CSRC)/build/capi.o $(CSRC)/build/msm.o $(CSRC)/build/msm_acc_compact.o $(CSRC)/build/msm_acc_regs.o $(CSRC)/build/msm_reduce.o $(CSRC)/build/srs.o $(CSRC)/build/poly.o $(CSRC)/build/prove.o $(CSRC)/build/selftest.o $(CSRC)/build/g2srs.o
+OBJS := $(CSRC)/build/capi.o $(CSRC)/build/msm.o $(CSRC)/build/msm_acc_compact.o $(CSRC)/build/msm_acc_regs.o $(CSRC)/build/msm_acc_affine.o $(CSRC)/build/msm_reduce.o $(CSRC)/build/srs.o $(CSRC)/build/poly.o $(CSRC)/build/prove.o $(CSRC)/build/selftest.o $(CSRC)/build/g2srs.o
 HDRS := $(wildcard $(CSRC)/*.cuh) $(CSRC)/internal.h include/sonic_b200.h
 
 all: sonic_b200/libsonic_b200.so oracle

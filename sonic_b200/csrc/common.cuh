@@ -118,6 +118,7 @@ struct Ctx {
     uint64_t launches = 0;
     int opt_window_bits = 0;
     int opt_chunk = 0;
+    int opt_aff_fused = 0;                                // affine accumulation: 0 prefix / inverses / add kernels per round, 1 one kernel per round with the inversion inside the block (measured 2x slower)
     int opt_heavy_mode = 1;                               // 1 one 128-thread block per heavy bucket (default), 0 by quads in two steps (measured: no gain at 8 GPUs, 0.27 -> 0.47 ms on one)
     int opt_overlap = 0;                                  // 1: two MSM batches per proof on two streams (tail of the first under the accumulation of the second); measured slower, off
     int opt_chunk_max = 0;                                // longest chunk the automatic rule may pick (0 = default)

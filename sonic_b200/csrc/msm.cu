@@ -384,13 +384,19 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const u
     }
     mark(1);
 
-    const uint32_t chunks = div_up(total_max, p.L);
+    const bool affine = cx.opt_acc_mode == 2;
+    const uint32_t chunks = affine ? 0u : div_up(total_max, p.L);
     G1XYZZ* buckets = ar.get<G1XYZZ>(p.GB);
     G1XYZZ* head = ar.get<G1XYZZ>(chunks ? chunks : 1);
     G1XYZZ* tail = ar.get<G1XYZZ>(chunks ? chunks : 1);
     if (sync && sync->wait_before_acc) SONIC_CUDA(cudaStreamWaitEvent(st, sync->wait_before_acc, 0));
     mark(4);
-    if (chunks) {
+    if (affine) {
+        // mean entries per bucket of the longest job: its W digits land in `sets` bucket sets of B buckets
+        double mean = 1.0;
+        for (int i = 0; i < M; ++i) mean = std::max(mean, (double)jobs[i].n * p.W / ((double)p.sets * p.B));
+        launch_accumulate_affine(cx, total_max, entries, offsets, p.GB, d_points, buckets, mean);
+    } else if (chunks) {
         if (cx.opt_acc_mode == 1) launch_accumulate_compact(cx, chunks, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
         else launch_accumulate_regs(cx, chunks, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
     }
@@ -412,7 +418,7 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const u
         cx.msm_offsets_total2 = offsets + p.GB;
         cx.msm_second_half = true;
     }
-    msm_reduce_stage(cx, p, M, offsets, chunks, buckets, head, tail, d_out_aff, d_out_comp, second ? E[2] : cx.ev[2]);
+    msm_reduce_stage(cx, p, M, offsets, chunks, buckets, head, tail, d_out_aff, d_out_comp, second ? E[2] : cx.ev[2], affine);
     mark(3);
 }
 

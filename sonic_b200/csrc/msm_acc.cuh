@@ -24,8 +24,13 @@ void launch_accumulate_regs(Ctx& cx, uint32_t chunks, const uint32_t* entries, c
 void launch_accumulate_compact(Ctx& cx, uint32_t chunks, const uint32_t* entries, const uint32_t* offsets, uint32_t GB, uint32_t L,
                                const G1Affine* points, G1XYZZ* buckets, G1XYZZ* head, G1XYZZ* tail);
 
+// acc_mode 2 (msm_acc_affine.cu): pairwise tree reduction of the buckets in affine coordinates with batched
+// inversions; leaves every bucket final (no head / tail pieces, no fix-up)
+void launch_accumulate_affine(Ctx& cx, uint64_t entries_max, const uint32_t* entries, const uint32_t* offsets, uint32_t GB,
+                              const G1Affine* points, G1XYZZ* buckets, double max_mean_bucket);
+
 // stages 5-7 (msm_reduce.cu)
 void msm_reduce_stage(Ctx& cx, const MsmPlan& p, int M, const uint32_t* offsets, uint32_t chunks, G1XYZZ* buckets,
-                      const G1XYZZ* head, const G1XYZZ* tail, G1Affine* d_out_aff, uint8_t* d_out_comp, cudaEvent_t fixup_done);
+                      const G1XYZZ* head, const G1XYZZ* tail, G1Affine* d_out_aff, uint8_t* d_out_comp, cudaEvent_t fixup_done, bool buckets_final = false);
 
 }  // namespace sonic

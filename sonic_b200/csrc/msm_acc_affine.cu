@@ -1,0 +1,556 @@
+// Bucket accumulation in affine coordinates with batched inversions (`acc_mode=2`).
+//
+// The XYZZ kernels spend ~9 multiplications on every insertion (8M + 2S; 2 712 IMAD.WIDE executed).  An
+// affine addition needs 1/(x2 - x1) and then only 3 (lambda, lambda^2, y3); with Montgomery's trick the
+// inversion of MANY independent denominators costs 3 multiplications each plus one real inversion for the
+// lot.  Independent additions are what a pairwise tree reduction of the buckets offers: round r adds the
+// entries of every bucket two by two (all pairs of all buckets at once), halving every bucket, until a
+// bucket is down to one point.  ~6 multiplications per insertion instead of ~9, no chunk head/tail
+// pieces, no fix-up stage -- for ~0.5 KB of HBM traffic per insertion (the intermediate points and the
+// prefix products live in global memory; 60 GB per n = 2^16 proof).
+//
+// STATUS: a correct, tested prototype that does NOT beat the XYZZ kernel on a B200 (prove() at n = 2^16: bucket
+// stage 44.1 ms against 42.7 ms for XYZZ accumulate + fix-up + heavy buckets; profiles/r02l_affine_launches.csv):
+// the additions run at ~70 % of the multiplier pipe (dependent loads of a slot's inputs in front of every five
+// products), the denominator pass is bound by its gathers (1 product per 184 bytes moved), and the per-round
+// inversion kernel has a 0.1 ms floor.  Hence `acc_mode` stays 1; DESIGN.md section 4.2 has the numbers.
+//
+// One round = a prepare kernel (sizes of the round), an exclusive scan (work-slot offsets), and
+//   A  k_aff_prefix     thread = AF_M consecutive output slots: the denominators d (x2 - x1; 2y for a doubling;
+//                       1 where nothing is inverted) and their running product, stored per slot; the product
+//                       of a block's AF_T x AF_M denominators goes to block_tot[block]
+//   B  k_aff_inverses   ONE inversion per round: Montgomery's trick over the block totals (512 threads, a
+//                       product tree in shared memory, Euclid inverse of the root), inv_tot[block]
+//   C  k_aff_add        the block's product tree again, walked down from inv_tot[block] to 1/(thread's product);
+//                       back-substitution gives 1/d per slot, then lambda, x3, y3.  A bucket that is down to one
+//                       point is written to the bucket array (XYZZ with ZZ = ZZZ = 1), the rest to the round's
+//                       output buffer.
+// After R rounds (R from the longest job's mean bucket size, 4..12) every bucket of at most 2^R entries is done; what is left of longer ones (the
+// all-ones weight rows of the synthetic circuits produce 65 536-entry buckets) is summed by one block each.
+//
+// Exceptional cases are decided identically in A and C from the same data: a missing partner (odd count), the
+// infinity marker (0,0) on either side, P + P (doubling: d = 2y, lambda = 3x^2 / 2y) and P - P (infinity).  The
+// reference's bench trapdoor x = 1 makes every base the same point: doublings and cancellations really occur.
+#include <cmath>
+
+#include "msm_acc.cuh"
+
+namespace sonic {
+
+constexpr int AF_T = 128;               // threads per block of the A / C kernels
+constexpr int AF_M = 16;                // output slots per thread
+constexpr int AF_SLOTS = AF_T * AF_M;   // slots per block = denominators per block total
+constexpr int AF_MAX_ROUNDS = 12;
+constexpr int AF_BT = 1024;             // threads of the single block of kernel B
+constexpr int AF_LEFT_SERIAL = 16;      // a bucket left with at most this many points after the last round is summed by one thread
+
+// ---- round bookkeeping -------------------------------------------------------------------------------------
+// cnt[b] points of bucket b start at base[b] in the round's input; the round leaves n = ceil(cnt / 2) of them.
+// A bucket with n == 1 is finished by this round (its point goes to the bucket array) and has nothing in the next.
+__global__ void __launch_bounds__(256) k_aff_prepare_first(const uint32_t* __restrict__ offsets, uint32_t GB, uint32_t* __restrict__ base,
+                                                           uint32_t* __restrict__ cnt, uint32_t* __restrict__ n_out, G1XYZZ* __restrict__ buckets) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > GB) return;
+    if (b == GB) { n_out[GB] = 0; return; }
+    const uint32_t a = offsets[b], k = offsets[b + 1] - a;
+    base[b] = a;
+    cnt[b] = k;
+    n_out[b] = (k + 1) / 2;
+    if (k == 0) store_xyzz(buckets + b, G1XYZZ::inf());
+}
+
+__global__ void __launch_bounds__(256) k_aff_prepare_next(const uint32_t* __restrict__ cnt_prev, const uint32_t* __restrict__ wo_prev, uint32_t GB,
+                                                          uint32_t* __restrict__ base, uint32_t* __restrict__ cnt, uint32_t* __restrict__ n_out) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > GB) return;
+    if (b == GB) { n_out[GB] = 0; return; }
+    const uint32_t n_prev = (cnt_prev[b] + 1) / 2;
+    const uint32_t k = n_prev > 1 ? n_prev : 0;
+    base[b] = wo_prev[b];
+    cnt[b] = k;
+    n_out[b] = (k + 1) / 2;
+}
+
+// last bucket whose first work slot is <= s   (wo[0] = 0 <= s < wo[GB])
+SONIC_D uint32_t aff_find_bucket(const uint32_t* __restrict__ wo, uint32_t GB, uint32_t s) {
+    uint32_t lo = 0, hi = GB;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (wo[mid] <= s) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// the inputs of one output slot
+struct AffSlot {
+    uint32_t b;      // bucket
+    uint32_t i0;     // index of the first input
+    bool has2;       // a partner exists at i0 + 1
+    bool last;       // the bucket is down to one point after this round
+};
+
+SONIC_D AffSlot aff_slot(uint32_t s, uint32_t& b, const uint32_t* __restrict__ wo, const uint32_t* __restrict__ base,
+                         const uint32_t* __restrict__ cnt, uint32_t GB) {
+    if (s >= wo[b + 1]) {
+        ++b;
+        if (s >= wo[b + 1]) b = aff_find_bucket(wo, GB, s);   // a run of empty buckets
+    }
+    AffSlot r;
+    r.b = b;
+    const uint32_t local = s - wo[b], k = cnt[b];
+    r.i0 = base[b] + 2 * local;
+    r.has2 = 2 * local + 1 < k;
+    r.last = k <= 2;
+    return r;
+}
+
+// x of input i (the first 48 bytes of the point); FIRST: through the sorted entry list into the SRS tables
+template <bool FIRST>
+SONIC_D Fq aff_load_x(const uint32_t* __restrict__ entries, const G1Affine* __restrict__ pts, uint32_t i) {
+    const G1Affine* p = FIRST ? pts + (entries[i] & 0x7fffffffu) : pts + i;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    const uint4 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2);
+    Fq x;
+    x.l[0] = v0.x; x.l[1] = v0.y; x.l[2] = v0.z; x.l[3] = v0.w;
+    x.l[4] = v1.x; x.l[5] = v1.y; x.l[6] = v1.z; x.l[7] = v1.w;
+    x.l[8] = v2.x; x.l[9] = v2.y; x.l[10] = v2.z; x.l[11] = v2.w;
+    return x;
+}
+template <bool FIRST>
+SONIC_D Fq aff_load_y(const uint32_t* __restrict__ entries, const G1Affine* __restrict__ pts, uint32_t i) {
+    uint32_t e = 0;
+    const G1Affine* p;
+    if (FIRST) { e = entries[i]; p = pts + (e & 0x7fffffffu); } else { p = pts + i; }
+    const uint4* q = reinterpret_cast<const uint4*>(p) + 3;
+    const uint4 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2);
+    Fq y;
+    y.l[0] = v0.x; y.l[1] = v0.y; y.l[2] = v0.z; y.l[3] = v0.w;
+    y.l[4] = v1.x; y.l[5] = v1.y; y.l[6] = v1.z; y.l[7] = v1.w;
+    y.l[8] = v2.x; y.l[9] = v2.y; y.l[10] = v2.z; y.l[11] = v2.w;
+    if (FIRST && (e & 0x80000000u)) y = fp_neg(y);
+    return y;
+}
+
+// pull the point behind input i towards L2 (the gathers of the first round are DRAM-latency bound otherwise)
+template <bool FIRST>
+SONIC_D void aff_prefetch(const uint32_t* __restrict__ entries, const G1Affine* __restrict__ pts, uint32_t i, bool whole) {
+    const G1Affine* p = FIRST ? pts + (entries[i] & 0x7fffffffu) : pts + i;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    if (whole) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p) + 64));
+}
+
+// What a slot does, and the denominator it contributes to the batch (1 when nothing is inverted).  A point of G1
+// with x = 0 does not exist ((0, +-2) has order 3), so x == 0 identifies the infinity marker (0,0).
+enum { AK_COPY = 0, AK_TAKE2, AK_INF, AK_DBL, AK_ADD };
+template <bool FIRST>
+SONIC_D int aff_kind(const uint32_t* __restrict__ entries, const G1Affine* __restrict__ pts, const AffSlot& sl, const Fq& x1, Fq& d) {
+    d = Fq::one();
+    if (!sl.has2) return AK_COPY;
+    const Fq x2 = aff_load_x<FIRST>(entries, pts, sl.i0 + 1);
+    if (x2.is_zero()) return AK_COPY;     // P1 + inf
+    if (x1.is_zero()) return AK_TAKE2;    // inf + P2
+    if (x1 == x2) {
+        const Fq y1 = aff_load_y<FIRST>(entries, pts, sl.i0), y2 = aff_load_y<FIRST>(entries, pts, sl.i0 + 1);
+        if (y1 == y2 && !y1.is_zero()) { d = fp_dbl(y1); return AK_DBL; }
+        return AK_INF;                    // P - P
+    }
+    d = fp_sub(x2, x1);
+    return AK_ADD;
+}
+
+// ---- A: denominators and their running products -------------------------------------------------------------------
+template <bool FIRST>
+__global__ void __launch_bounds__(AF_T, 4)
+k_aff_prefix(const uint32_t* __restrict__ entries, const G1Affine* __restrict__ pts, const uint32_t* __restrict__ wo,
+             const uint32_t* __restrict__ base, const uint32_t* __restrict__ cnt, uint32_t GB, Fq* __restrict__ pre,
+             Fq* __restrict__ block_tot) {
+    __shared__ Fq tree[AF_T];
+    const uint32_t total = wo[GB];
+    if (blockIdx.x * (uint32_t)AF_SLOTS >= total) return;   // the whole block is beyond the round's slots (uniform)
+    const uint32_t s0 = (blockIdx.x * AF_T + threadIdx.x) * AF_M;
+    Fq run = Fq::one();
+    if (s0 < total) {
+        uint32_t b = aff_find_bucket(wo, GB, s0);
+        for (int j = 0; j < AF_M; ++j) {
+            const uint32_t s = s0 + j;
+            if (s >= total) break;
+            const AffSlot sl = aff_slot(s, b, wo, base, cnt, GB);
+            const Fq x1 = aff_load_x<FIRST>(entries, pts, sl.i0);
+            Fq d;
+            aff_kind<FIRST>(entries, pts, sl, x1, d);
+            run = fp_mul(run, d);
+            pre[s] = run;
+        }
+    }
+    // product of the block's thread totals
+    tree[threadIdx.x] = run;
+    __syncthreads();
+    for (int s = AF_T / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) tree[threadIdx.x] = fp_mul(tree[threadIdx.x], tree[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_tot[blockIdx.x] = tree[0];
+}
+
+// ---- B: the inverses of all block totals from ONE inversion ---------------------------------------------------------
+// thread t owns `per` consecutive totals: running products (kept in global scratch), a product tree over the thread
+// totals in shared memory, the Euclid inverse of the root, the tree walked back down, back-substitution.
+__global__ void __launch_bounds__(AF_BT)
+k_aff_inverses(const Fq* __restrict__ tot, const uint32_t* __restrict__ wo, uint32_t GB, Fq* __restrict__ scratch, Fq* __restrict__ inv) {
+    extern __shared__ uint32_t af_smem_raw[];
+    Fq* tree = reinterpret_cast<Fq*>(af_smem_raw);   // 2 * AF_BT nodes, node 1 = root, leaves at AF_BT + t
+    const uint32_t total = wo[GB];
+    const uint32_t nb = (total + AF_SLOTS - 1) / AF_SLOTS;
+    if (nb == 0) return;
+    const uint32_t per = (nb + AF_BT - 1) / AF_BT;
+    const uint32_t i0 = threadIdx.x * per, i1 = i0 + per < nb ? i0 + per : nb;
+    Fq run = Fq::one();
+    for (uint32_t i = i0; i < i1; ++i) {
+        run = fp_mul(run, tot[i]);
+        scratch[i] = run;
+    }
+    tree[AF_BT + threadIdx.x] = run;
+    __syncthreads();
+    for (int w = AF_BT / 2; w >= 1; w >>= 1) {   // nodes w .. 2w-1
+        if ((int)threadIdx.x < w) {
+            const int i = w + threadIdx.x;
+            tree[i] = fp_mul(tree[2 * i], tree[2 * i + 1]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tree[1] = fp_inv_euclid(tree[1]);
+    __syncthreads();
+    for (int w = 1; w <= AF_BT / 2; w <<= 1) {    // children of nodes w .. 2w-1
+        if ((int)threadIdx.x < w) {
+            const int i = w + threadIdx.x;
+            const Fq l = tree[2 * i], r = tree[2 * i + 1], iv = tree[i];
+            tree[2 * i] = fp_mul(iv, r);
+            tree[2 * i + 1] = fp_mul(iv, l);
+        }
+        __syncthreads();
+    }
+    Fq inv_run = tree[AF_BT + threadIdx.x];   // 1 / (product of this thread's totals)
+    for (uint32_t i = i1; i-- > i0;) {
+        const Fq prev = i > i0 ? scratch[i - 1] : Fq::one();
+        inv[i] = fp_mul(inv_run, prev);
+        inv_run = fp_mul(inv_run, tot[i]);
+    }
+}
+
+// ---- C: 1/d per slot, the additions ---------------------------------------------------------------------------------------
+template <bool FIRST>
+__global__ void __launch_bounds__(AF_T, 3)
+k_aff_add(const uint32_t* __restrict__ entries, const G1Affine* __restrict__ pts, const uint32_t* __restrict__ wo,
+          const uint32_t* __restrict__ base, const uint32_t* __restrict__ cnt, uint32_t GB, const Fq* __restrict__ pre,
+          const Fq* __restrict__ inv_tot, G1Affine* __restrict__ out, G1XYZZ* __restrict__ buckets) {
+    __shared__ Fq tree[2 * AF_T];   // node 1 = root, leaves at AF_T + t
+    const uint32_t total = wo[GB];
+    if (blockIdx.x * (uint32_t)AF_SLOTS >= total) return;
+    const uint32_t s0 = (blockIdx.x * AF_T + threadIdx.x) * AF_M;
+    const uint32_t s1 = s0 >= total ? s0 : (total - s0 < (uint32_t)AF_M ? total : s0 + AF_M);   // this thread's slots [s0, s1)
+    // 1 / (this thread's product): the block's product tree, walked down from the inverse of its root
+    tree[AF_T + threadIdx.x] = s1 > s0 ? pre[s1 - 1] : Fq::one();
+    __syncthreads();
+    for (int w = AF_T / 2; w >= 1; w >>= 1) {
+        if ((int)threadIdx.x < w) {
+            const int i = w + threadIdx.x;
+            tree[i] = fp_mul(tree[2 * i], tree[2 * i + 1]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tree[1] = inv_tot[blockIdx.x];
+    __syncthreads();
+    for (int w = 1; w <= AF_T / 2; w <<= 1) {
+        if ((int)threadIdx.x < w) {
+            const int i = w + threadIdx.x;
+            const Fq l = tree[2 * i], r = tree[2 * i + 1], iv = tree[i];
+            tree[2 * i] = fp_mul(iv, r);
+            tree[2 * i + 1] = fp_mul(iv, l);
+        }
+        __syncthreads();
+    }
+    if (s1 <= s0) return;
+    Fq inv_run = tree[AF_T + threadIdx.x];
+    // the slots' buckets, forwards (the walk needs ascending slots); the additions then run backwards
+    uint32_t bs[AF_M];
+    {
+        uint32_t b = aff_find_bucket(wo, GB, s0);
+        for (int j = 0; j < AF_M; ++j) {
+            const uint32_t s = s0 + j;
+            if (s >= s1) break;
+            if (s >= wo[b + 1]) {
+                ++b;
+                if (s >= wo[b + 1]) b = aff_find_bucket(wo, GB, s);
+            }
+            bs[j] = b;
+            if (FIRST) {
+                const uint32_t local = s - wo[b], k = cnt[b], i0 = base[b] + 2 * local;
+                aff_prefetch<FIRST>(entries, pts, i0, true);
+                if (2 * local + 1 < k) aff_prefetch<FIRST>(entries, pts, i0 + 1, true);
+            }
+        }
+    }
+    for (int j = AF_M - 1; j >= 0; --j) {
+        const uint32_t s = s0 + j;
+        if (s >= s1) continue;
+        uint32_t b = bs[j];
+        const AffSlot sl = aff_slot(s, b, wo, base, cnt, GB);
+        const Fq x1 = aff_load_x<FIRST>(entries, pts, sl.i0);
+        Fq d;
+        const int kind = aff_kind<FIRST>(entries, pts, sl, x1, d);
+        const Fq prev = j > 0 ? pre[s - 1] : Fq::one();
+        const Fq inv_d = fp_mul(inv_run, prev);
+        inv_run = fp_mul(inv_run, d);
+        G1Affine r;
+        if (kind == AK_COPY) {
+            r.x = x1;
+            r.y = aff_load_y<FIRST>(entries, pts, sl.i0);
+        } else if (kind == AK_TAKE2) {
+            r.x = aff_load_x<FIRST>(entries, pts, sl.i0 + 1);
+            r.y = aff_load_y<FIRST>(entries, pts, sl.i0 + 1);
+        } else if (kind == AK_INF) {
+            r = G1Affine::inf();
+        } else {
+            const Fq y1 = aff_load_y<FIRST>(entries, pts, sl.i0);
+            Fq lambda, x2;
+            if (kind == AK_DBL) {
+                const Fq xx = fp_sqr(x1);
+                lambda = fp_mul(fp_add(fp_dbl(xx), xx), inv_d);   // 3 x^2 / 2y
+                x2 = x1;
+            } else {
+                x2 = aff_load_x<FIRST>(entries, pts, sl.i0 + 1);
+                const Fq y2 = aff_load_y<FIRST>(entries, pts, sl.i0 + 1);
+                lambda = fp_mul(fp_sub(y2, y1), inv_d);
+            }
+            r.x = fp_sub(fp_sub(fp_sqr(lambda), x1), x2);
+            r.y = fp_sub(fp_mul(lambda, fp_sub(x1, r.x)), y1);
+        }
+        if (sl.last) store_xyzz(buckets + sl.b, G1XYZZ::from_affine(r));
+        else out[s] = r;
+    }
+}
+
+// ---- A + B + C in one kernel: the inversion stays inside the block ----------------------------------------------------------
+// (Option `aff_fused` = 1; NOT the default: measured 88 ms against 44 ms for the split form on a n = 2^16 proof.)  The
+// split form reads every input twice from global memory (x for the denominators, then the whole points), stores and
+// re-reads a 48-byte running product per slot and needs kernel B between the two halves.  Here a block of AF_T threads
+// x AF_FM slots keeps the running products in shared memory (thread-minor columns, conflict-free), builds its product
+// tree once, lets ONE thread invert the root (binary Euclid) while the block's other warps wait at the barrier, and
+// goes straight on to the additions.  With 61 KB of shared memory only three blocks fit an SM, and three are not
+// enough to cover one another's inversions: the multiplier pipe idles half of the time.
+constexpr int AF_FM = 8;
+constexpr int AF_FSLOTS = AF_T * AF_FM;
+constexpr size_t AF_FSMEM = (size_t)AF_FM * 12 * AF_T * 4 + 2 * (size_t)AF_T * sizeof(Fq);
+
+SONIC_D void aff_col_store(uint32_t* __restrict__ col, int j, const Fq& v) {
+#pragma unroll
+    for (int l = 0; l < 12; ++l) col[(j * 12 + l) * AF_T] = v.l[l];
+}
+SONIC_D Fq aff_col_load(const uint32_t* __restrict__ col, int j) {
+    Fq v;
+#pragma unroll
+    for (int l = 0; l < 12; ++l) v.l[l] = col[(j * 12 + l) * AF_T];
+    return v;
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(AF_T, 3)
+k_aff_fused(const uint32_t* __restrict__ entries, const G1Affine* __restrict__ pts, const uint32_t* __restrict__ wo,
+            const uint32_t* __restrict__ base, const uint32_t* __restrict__ cnt, uint32_t GB, G1Affine* __restrict__ out,
+            G1XYZZ* __restrict__ buckets) {
+    extern __shared__ uint32_t af_dyn[];
+    uint32_t* col = af_dyn + threadIdx.x;                                                   // this thread's column of running products
+    Fq* tree = reinterpret_cast<Fq*>(af_dyn + (size_t)AF_FM * 12 * AF_T);                  // node 1 = root, leaves at AF_T + t
+    const uint32_t total = wo[GB];
+    if (blockIdx.x * (uint32_t)AF_FSLOTS >= total) return;
+    const uint32_t s0 = (blockIdx.x * AF_T + threadIdx.x) * AF_FM;
+    const uint32_t s1 = s0 >= total ? s0 : (total - s0 < (uint32_t)AF_FM ? total : s0 + AF_FM);
+    uint32_t bs[AF_FM];
+    Fq run = Fq::one();
+    if (s1 > s0) {
+        uint32_t b = aff_find_bucket(wo, GB, s0);
+#pragma unroll
+        for (int j = 0; j < AF_FM; ++j) {
+            const uint32_t s = s0 + j;
+            if (s < s1) {
+                const AffSlot sl = aff_slot(s, b, wo, base, cnt, GB);
+                bs[j] = b;
+                const Fq x1 = aff_load_x<FIRST>(entries, pts, sl.i0);
+                Fq d;
+                aff_kind<FIRST>(entries, pts, sl, x1, d);
+                run = fp_mul(run, d);
+                aff_col_store(col, j, run);
+            }
+        }
+    }
+    tree[AF_T + threadIdx.x] = run;
+    __syncthreads();
+    for (int w = AF_T / 2; w >= 1; w >>= 1) {
+        if ((int)threadIdx.x < w) {
+            const int i = w + threadIdx.x;
+            tree[i] = fp_mul(tree[2 * i], tree[2 * i + 1]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tree[1] = fp_inv_euclid(tree[1]);
+    __syncthreads();
+    for (int w = 1; w <= AF_T / 2; w <<= 1) {
+        if ((int)threadIdx.x < w) {
+            const int i = w + threadIdx.x;
+            const Fq l = tree[2 * i], r = tree[2 * i + 1], iv = tree[i];
+            tree[2 * i] = fp_mul(iv, r);
+            tree[2 * i + 1] = fp_mul(iv, l);
+        }
+        __syncthreads();
+    }
+    if (s1 <= s0) return;
+    Fq inv_run = tree[AF_T + threadIdx.x];
+#pragma unroll
+    for (int j = AF_FM - 1; j >= 0; --j) {
+        const uint32_t s = s0 + j;
+        if (s >= s1) continue;
+        uint32_t b = bs[j];
+        const AffSlot sl = aff_slot(s, b, wo, base, cnt, GB);
+        const Fq x1 = aff_load_x<FIRST>(entries, pts, sl.i0);
+        Fq d;
+        const int kind = aff_kind<FIRST>(entries, pts, sl, x1, d);
+        const Fq prev = j > 0 ? aff_col_load(col, j > 0 ? j - 1 : 0) : Fq::one();
+        const Fq inv_d = fp_mul(inv_run, prev);
+        inv_run = fp_mul(inv_run, d);
+        G1Affine r;
+        if (kind == AK_COPY) {
+            r.x = x1;
+            r.y = aff_load_y<FIRST>(entries, pts, sl.i0);
+        } else if (kind == AK_TAKE2) {
+            r.x = aff_load_x<FIRST>(entries, pts, sl.i0 + 1);
+            r.y = aff_load_y<FIRST>(entries, pts, sl.i0 + 1);
+        } else if (kind == AK_INF) {
+            r = G1Affine::inf();
+        } else {
+            const Fq y1 = aff_load_y<FIRST>(entries, pts, sl.i0);
+            Fq lambda, x2;
+            if (kind == AK_DBL) {
+                const Fq xx = fp_sqr(x1);
+                lambda = fp_mul(fp_add(fp_dbl(xx), xx), inv_d);
+                x2 = x1;
+            } else {
+                x2 = aff_load_x<FIRST>(entries, pts, sl.i0 + 1);
+                const Fq y2 = aff_load_y<FIRST>(entries, pts, sl.i0 + 1);
+                lambda = fp_mul(fp_sub(y2, y1), inv_d);
+            }
+            r.x = fp_sub(fp_sub(fp_sqr(lambda), x1), x2);
+            r.y = fp_sub(fp_mul(lambda, fp_sub(x1, r.x)), y1);
+        }
+        if (sl.last) store_xyzz(buckets + sl.b, G1XYZZ::from_affine(r));
+        else out[s] = r;
+    }
+}
+
+// ---- what is left of buckets longer than 2^R entries -----------------------------------------------------------------------
+// a few points: the thread that finds them sums them; many (a 65 536-entry bucket still has hundreds): one block each
+__global__ void __launch_bounds__(128) k_aff_left_list(const uint32_t* __restrict__ cnt_prev, const uint32_t* __restrict__ wo_prev,
+                                                       const G1Affine* __restrict__ pts, uint32_t GB, uint32_t* __restrict__ count,
+                                                       uint32_t* __restrict__ list, G1XYZZ* __restrict__ buckets) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= GB) return;
+    const uint32_t n = (cnt_prev[b] + 1) / 2;   // points the last round left for this bucket (1 = already final)
+    if (n <= 1) return;
+    if (n > (uint32_t)AF_LEFT_SERIAL) { list[atomicAdd(count, 1u)] = b; return; }
+    G1XYZZ acc = G1XYZZ::inf();
+    const uint32_t first = wo_prev[b];
+    for (uint32_t i = 0; i < n; ++i) g1_madd(acc, load_affine(pts + first + i));
+    store_xyzz(buckets + b, acc);
+}
+
+template <int THREADS>
+SONIC_D G1XYZZ aff_block_sum(G1XYZZ v, G1XYZZ* smem) {
+    smem[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            g1_add(v, smem[threadIdx.x + s]);
+            smem[threadIdx.x] = v;
+        }
+        __syncthreads();
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(MSM_RED_THREADS)
+k_aff_left_sum(const uint32_t* __restrict__ cnt_prev, const uint32_t* __restrict__ wo_prev, const G1Affine* __restrict__ pts,
+               const uint32_t* __restrict__ count, const uint32_t* __restrict__ list, G1XYZZ* __restrict__ buckets) {
+    __shared__ G1XYZZ smem[MSM_RED_THREADS];
+    const uint32_t nl = *count;
+    for (uint32_t h = blockIdx.x; h < nl; h += gridDim.x) {
+        const uint32_t b = list[h];
+        const uint32_t n = (cnt_prev[b] + 1) / 2, first = wo_prev[b];
+        G1XYZZ acc = G1XYZZ::inf();
+        for (uint32_t i = threadIdx.x; i < n; i += MSM_RED_THREADS) g1_madd(acc, load_affine(pts + first + i));
+        acc = aff_block_sum<MSM_RED_THREADS>(acc, smem);
+        if (threadIdx.x == 0) store_xyzz(buckets + b, acc);
+        __syncthreads();
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------------
+// entries sorted by bucket (offsets[GB+1], at most `entries_max` of them) -> buckets[GB]
+void launch_accumulate_affine(Ctx& cx, uint64_t entries_max, const uint32_t* entries, const uint32_t* offsets, uint32_t GB,
+                              const G1Affine* points, G1XYZZ* buckets, double max_mean_bucket) {
+    Arena& ar = cx.arena;
+    // rounds: enough for a bucket six standard deviations above the longest job's mean size
+    int AF_ROUNDS = 4;
+    while (AF_ROUNDS < AF_MAX_ROUNDS && (double)(1u << AF_ROUNDS) < max_mean_bucket + 6.0 * sqrt(max_mean_bucket) + 2.0) ++AF_ROUNDS;
+    // upper bounds of the work slots per round: every bucket halves, rounding up
+    uint64_t smax[AF_MAX_ROUNDS];
+    uint64_t prev = entries_max;
+    for (int r = 0; r < AF_ROUNDS; ++r) {
+        smax[r] = (prev + GB) / 2 + 1;
+        prev = smax[r];
+    }
+    uint32_t* base[2] = {ar.get<uint32_t>((size_t)GB + 1), ar.get<uint32_t>((size_t)GB + 1)};
+    uint32_t* cnt[2] = {ar.get<uint32_t>((size_t)GB + 1), ar.get<uint32_t>((size_t)GB + 1)};
+    uint32_t* wo[2] = {ar.get<uint32_t>((size_t)GB + 1), ar.get<uint32_t>((size_t)GB + 1)};
+    G1Affine* buf[2] = {ar.get<G1Affine>(smax[0]), ar.get<G1Affine>(AF_ROUNDS > 1 ? smax[1] : 1)};
+    Fq* pre = ar.get<Fq>(smax[0]);
+    const uint64_t nb_max = (smax[0] + AF_SLOTS - 1) / AF_SLOTS;
+    Fq* tot = ar.get<Fq>(nb_max);
+    Fq* inv = ar.get<Fq>(nb_max);
+    Fq* scratch = ar.get<Fq>(nb_max);
+    const size_t b_smem = 2 * (size_t)AF_BT * sizeof(Fq);
+    SONIC_CUDA(cudaFuncSetAttribute(k_aff_inverses, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b_smem));
+    SONIC_CUDA(cudaFuncSetAttribute(k_aff_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AF_FSMEM));
+    SONIC_CUDA(cudaFuncSetAttribute(k_aff_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AF_FSMEM));
+    for (int r = 0; r < AF_ROUNDS; ++r) {
+        const int cur = r & 1, prv = cur ^ 1;
+        if (r == 0) SONIC_LAUNCH(k_aff_prepare_first, div_up((uint64_t)GB + 1, 256), 256, 0, offsets, GB, base[cur], cnt[cur], wo[cur], buckets);
+        else SONIC_LAUNCH(k_aff_prepare_next, div_up((uint64_t)GB + 1, 256), 256, 0, cnt[prv], wo[prv], GB, base[cur], cnt[cur], wo[cur]);
+        exclusive_scan_u32(ar, wo[cur], wo[cur], GB + 1);
+        G1Affine* out = buf[cur];
+        if (cx.opt_aff_fused) {
+            const unsigned fblocks = div_up(smax[r], AF_FSLOTS);
+            if (r == 0) SONIC_LAUNCH(k_aff_fused<true>, fblocks, AF_T, AF_FSMEM, entries, points, wo[cur], base[cur], cnt[cur], GB, out, buckets);
+            else SONIC_LAUNCH(k_aff_fused<false>, fblocks, AF_T, AF_FSMEM, (const uint32_t*)nullptr, (const G1Affine*)buf[prv], wo[cur], base[cur], cnt[cur], GB, out, buckets);
+            continue;
+        }
+        const unsigned blocks = div_up(smax[r], AF_SLOTS);
+        if (r == 0) {
+            SONIC_LAUNCH(k_aff_prefix<true>, blocks, AF_T, 0, entries, points, wo[cur], base[cur], cnt[cur], GB, pre, tot);
+            SONIC_LAUNCH(k_aff_inverses, 1, AF_BT, b_smem, tot, wo[cur], GB, scratch, inv);
+            SONIC_LAUNCH(k_aff_add<true>, blocks, AF_T, 0, entries, points, wo[cur], base[cur], cnt[cur], GB, pre, inv, out, buckets);
+        } else {
+            const G1Affine* in = buf[prv];
+            SONIC_LAUNCH(k_aff_prefix<false>, blocks, AF_T, 0, (const uint32_t*)nullptr, in, wo[cur], base[cur], cnt[cur], GB, pre, tot);
+            SONIC_LAUNCH(k_aff_inverses, 1, AF_BT, b_smem, tot, wo[cur], GB, scratch, inv);
+            SONIC_LAUNCH(k_aff_add<false>, blocks, AF_T, 0, (const uint32_t*)nullptr, in, wo[cur], base[cur], cnt[cur], GB, pre, inv, out, buckets);
+        }
+    }
+    // buckets that still hold more than one point after the last round
+    const int last = (AF_ROUNDS - 1) & 1;
+    uint32_t* left_count = ar.get<uint32_t>(1);
+    uint32_t* left_list = ar.get<uint32_t>((size_t)GB);
+    SONIC_CUDA(cudaMemsetAsync(left_count, 0, 4, cx.stream));
+    SONIC_LAUNCH(k_aff_left_list, div_up(GB, 128), 128, 0, cnt[last], wo[last], buf[last], GB, left_count, left_list, buckets);
+    SONIC_LAUNCH(k_aff_left_sum, cx.sm_count * 2, MSM_RED_THREADS, 0, cnt[last], wo[last], buf[last], left_count, left_list, buckets);
+}
+
+}  // namespace sonic

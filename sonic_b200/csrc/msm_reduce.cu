@@ -328,9 +328,10 @@ k_msm_finish(const G1XYZZ* __restrict__ partial, uint32_t S, int W, int c, G1Aff
 
 // ---- host side ---------------------------------------------------------------------------
 void msm_reduce_stage(Ctx& cx, const MsmPlan& p, int M, const uint32_t* offsets, uint32_t chunks, G1XYZZ* buckets,
-                      const G1XYZZ* head, const G1XYZZ* tail, G1Affine* d_out_aff, uint8_t* d_out_comp, cudaEvent_t fixup_done) {
+                      const G1XYZZ* head, const G1XYZZ* tail, G1Affine* d_out_aff, uint8_t* d_out_comp, cudaEvent_t fixup_done, bool buckets_final) {
     Arena& ar = cx.arena;
     cudaStream_t st = cx.stream;
+    if (!buckets_final) {
     uint32_t* heavy_count = ar.get<uint32_t>(1);
     const size_t heavy_max = (size_t)chunks / MSM_HEAVY_PIECES + 2;
     uint32_t* heavy_list = ar.get<uint32_t>(heavy_max);
@@ -342,6 +343,7 @@ void msm_reduce_stage(Ctx& cx, const MsmPlan& p, int M, const uint32_t* offsets,
         SONIC_LAUNCH(k_msm_heavy_fin, div_up(heavy_max * 4, 128), 128, 0, heavy_count, heavy_list, parts, buckets);
     } else {
         SONIC_LAUNCH(k_msm_heavy, cx.sm_count * 2, MSM_RED_THREADS, 0, offsets, p.L, buckets, head, tail, heavy_count, heavy_list);
+    }
     }
     SONIC_CUDA(cudaEventRecord(fixup_done, st));
 

@@ -64,10 +64,11 @@ def test_msm_result_independent_of_tuning_options(gpu, big_srs):
                 gpu.set_option("chunk", chunk)
                 results.add(gpu.msm(srs, 0, -(N // 2), sc))
             # the variants of the tail stages (quads of lanes / one thread per K buckets / level by level; heavy buckets
-            # by quads or by one block each) and the accumulate kernel with the operands in registers
+            # by quads or by one block each), the accumulate kernel with the operands in registers, and the bucket stage in
+            # affine coordinates with batched inversions (split and fused forms)
             gpu.set_option("window_bits", 0)
             gpu.set_option("chunk", 0)
-            for name, values in (("reduce_mode", (1, 2, 3, 0)), ("heavy_mode", (0, 1)), ("acc_mode", (0, 1))):
+            for name, values in (("reduce_mode", (1, 2, 3, 0)), ("heavy_mode", (0, 1)), ("acc_mode", (0, 2)), ("aff_fused", (1, 0)), ("acc_mode", (1,))):
                 for v in values:
                     gpu.set_option(name, v)
                     results.add(gpu.msm(srs, 0, -(N // 2), sc))
@@ -79,6 +80,7 @@ def test_msm_result_independent_of_tuning_options(gpu, big_srs):
         gpu.set_option("reduce_mode", 0)
         gpu.set_option("heavy_mode", 1)
         gpu.set_option("acc_mode", 1)
+        gpu.set_option("aff_fused", 0)
     assert len(results) == 1
     assert results.pop() == C(bls.g1_mul_gen(_horner_window(sc, x, -(N // 2))))
 
