@@ -10,7 +10,8 @@
 // prefix products live in global memory; 60 GB per n = 2^16 proof).
 //
 // STATUS: a correct, tested prototype that does NOT beat the XYZZ kernel on a B200 (prove() at n = 2^16: bucket
-// stage 44.1 ms against 42.7 ms for XYZZ accumulate + fix-up + heavy buckets; profiles/r02l_affine_launches.csv):
+// stage 42.6 ms against 42.7 ms for XYZZ accumulate + fix-up + heavy buckets -- a tie; 2^24-point MSM 79.1 against
+// 74.8 ms; profiles/r02n_affine_vs_xyzz.json, r02n_affine_ncu.md):
 // the additions run at ~70 % of the multiplier pipe (dependent loads of a slot's inputs in front of every five
 // products), the denominator pass is bound by its gathers (1 product per 184 bytes moved), and the per-round
 // inversion kernel has a 0.1 ms floor.  Hence `acc_mode` stays 1; DESIGN.md section 4.2 has the numbers.
