@@ -172,7 +172,7 @@ int sonic_prove_batch(const sonic_srs* srs, const sonic_circuit* circuit, uint64
 /* One proof sharded over `world` PROCESSES (one per GPU; the multi-process twin of sonic_init with
  * ndev > 1).  Every rank calls sonic_prove_shard with the same inputs.  The exponent windows of the
  * proof's 4Q+7 MSMs, concatenated in record order, are cut into `world` runs of terms (equal, except
- * that the ranks that also build t(X,y) get n/2 terms less): a rank sums a few whole MSMs plus at
+ * that the ranks that also build t(X,y) get up to n/2 terms less (n/2 * min(world-2, 6)/6)): a rank sums a few whole MSMs plus at
  * most two partial ones (the identity for the rest) and builds only the polynomials, power tables and
  * openings those MSMs need; a field value of the proof is computed by the lowest rank that opens the
  * polynomial it belongs to.  The result is an exchange record of sonic_shard_exchange_size(Q) bytes:

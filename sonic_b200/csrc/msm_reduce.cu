@@ -350,8 +350,9 @@ void msm_reduce_stage(Ctx& cx, const MsmPlan& p, int M, const uint32_t* offsets,
     // Automatic (reduce_mode 0): quads while the stage is latency-bound -- few bucket sets: a standalone MSM, a small
     // proof, one rank's share of a sharded proof (one job of 2^15 buckets: 0.97 -> 0.55 ms; prove at n = 2^13: 1.33 -> 0.95) --
     // and one thread per K buckets once there are enough buckets to fill the multiplier pipe without help (39 sets of
-    // 2^15: 2.58 ms against 2.74 with quads).
-    const bool quads = cx.opt_reduce_mode == 3 || (cx.opt_reduce_mode == 0 && (uint64_t)M * p.sets * p.B <= (1ull << 19));
+    // 2^15: 2.52 ms against 2.72 with quads; 17 / 23 sets, a rank of two: 1.86 / 1.93 against 1.48 / 1.74 -- the switch
+    // sits at 2^20 buckets).
+    const bool quads = cx.opt_reduce_mode == 3 || (cx.opt_reduce_mode == 0 && (uint64_t)M * p.sets * p.B <= (1ull << 20));
     if (quads) {
         // quads of lanes share every point operation.  K buckets per quad, as large as keeping ALL blocks
         // resident at once allows (RQ_MINB per SM): a second wave would double the time of this latency-bound stage.

@@ -763,7 +763,9 @@ int prove_enqueue(Ctx& cx, SrsRep& srs, const CircuitRep& circ_, const Fr* d_in,
             return o;
         };
         if (sharded && has_main) {
-            const uint64_t V = (uint64_t)n / 2;
+            // (n/2 at eight ranks, where the t-owners hold 4 long MSMs against 6-7 short ones elsewhere; nothing at two, where
+            // the t-owner's extra polynomial work and the other rank's extra bucket sets cancel: measured per rank)
+            const uint64_t V = (uint64_t)n / 2 * std::min<uint64_t>(W_ > 2 ? W_ - 2 : 0, 6) / 6;
             const std::vector<char> o1 = t_owners(bound);
             uint64_t k = 0;
             for (char c : o1) k += c;

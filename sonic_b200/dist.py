@@ -29,7 +29,7 @@ def deal_terms(lengths: Sequence[int], world: int, t_msms: Sequence[int] = (), t
     A rank owns a few whole MSMs and at most two partial ones; at most world-1 MSMs are split; a boundary
     never leaves a sliver of an MSM (fewer than min(len/2, max(4096, total/(64 world))) terms) on either side.
     The runs are equal, except that ranks owning part of the MSMs `t_msms` (prT and prWt, records 1
-    and 4 of `prove`: those ranks also build t(X,y)) are dealt `t_extra` (= n/2) terms less when
+    and 4 of `prove`: those ranks also build t(X,y)) are dealt `t_extra` (= n/2 * min(world - 2, 6) / 6) terms less when
     that leaves the same ranks in charge of them."""
     total = sum(lengths)
     pos = [0]
