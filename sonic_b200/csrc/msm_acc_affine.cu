@@ -9,29 +9,12 @@
 // pieces, no fix-up stage -- for ~0.5 KB of HBM traffic per insertion (the intermediate points and the
 // prefix products live in global memory; 60 GB per n = 2^16 proof).
 //
-// STATUS: a correct, tested prototype that does NOT beat the XYZZ kernel on a B200 (prove() at n = 2^16: bucket
-// stage 42.6 ms against 42.7 ms for XYZZ accumulate + fix-up + heavy buckets -- a tie; 2^24-point MSM 79.1 against
-// 74.8 ms; profiles/r02n_affine_vs_xyzz.json, r02n_affine_ncu.md):
-// the additions run at ~70 % of the multiplier pipe (dependent loads of a slot's inputs in front of every five
-// products), the denominator pass is bound by its gathers (1 product per 184 bytes moved), and the per-round
-// inversion kernel has a 0.1 ms floor.  Hence `acc_mode` stays 1; DESIGN.md section 4.2 has the numbers.
-//
-// One round = a prepare kernel (sizes of the round), an exclusive scan (work-slot offsets), and
-//   A  k_aff_prefix     thread = AF_M consecutive output slots: the denominators d (x2 - x1; 2y for a doubling;
-//                       1 where nothing is inverted) and their running product, stored per slot; the product
-//                       of a block's AF_T x AF_M denominators goes to block_tot[block]
-//   B  k_aff_inverses   ONE inversion per round: Montgomery's trick over the block totals (512 threads, a
-//                       product tree in shared memory, Euclid inverse of the root), inv_tot[block]
-//   C  k_aff_add        the block's product tree again, walked down from inv_tot[block] to 1/(thread's product);
-//                       back-substitution gives 1/d per slot, then lambda, x3, y3.  A bucket that is down to one
-//                       point is written to the bucket array (XYZZ with ZZ = ZZZ = 1), the rest to the round's
-//                       output buffer.
-// After R rounds (R from the longest job's mean bucket size, 4..12) every bucket of at most 2^R entries is done; what is left of longer ones (the
-// all-ones weight rows of the synthetic circuits produce 65 536-entry buckets) is summed by one block each.
-//
-// Exceptional cases are decided identically in A and C from the same data: a missing partner (odd count), the
-// infinity marker (0,0) on either side, P + P (doubling: d = 2y, lambda = 3x^2 / 2y) and P - P (infinity).  The
-// reference's bench trapdoor x = 1 makes every base the same point: doublings and cancellations really occur.
+// STATUS: correct (every parity test, the golden proofs and the x = 1 trapdoor pass with SONIC_ACC_MODE=2) and about as
+// fast as the XYZZ kernel on a B200 (profiles/r02n_affine_vs_xyzz.json, r02n_affine_ncu.md): prove() at n = 2^16 47.3 ms
+// against 48.8 ms (it needs no fix-up stage), the 2^24-point MSM 82.8 against 81.6 ms, one rank of an 8-way sharded
+// proof 7.4 against 5.9 ms (nine rounds of small kernels).  The additions run at 60-70 % of the multiplier pipe
+// (barrier stalls of the block product tree, instruction-cache misses, dependent loads in front of every five
+// products); the denominator pass is bound by its gathers.  `acc_mode` therefore stays 1; DESIGN.md section 4.2.
 #include <cmath>
 
 #include "msm_acc.cuh"
@@ -39,7 +22,7 @@
 namespace sonic {
 
 constexpr int AF_T = 128;               // threads per block of the A / C kernels
-constexpr int AF_M = 16;                // output slots per thread
+constexpr int AF_M = 32;                // output slots per thread
 constexpr int AF_SLOTS = AF_T * AF_M;   // slots per block = denominators per block total
 constexpr int AF_MAX_ROUNDS = 12;
 constexpr int AF_BT = 1024;             // threads of the single block of kernel B
@@ -432,7 +415,7 @@ k_aff_fused(const uint32_t* __restrict__ entries, const G1Affine* __restrict__ p
             Fq lambda, x2;
             if (kind == AK_DBL) {
                 const Fq xx = fp_sqr(x1);
-                lambda = fp_mul(fp_add(fp_dbl(xx), xx), inv_d);
+                lambda = fp_mul(fp_add(fp_dbl(xx), xx), inv_d);   // 3 x^2 / 2y
                 x2 = x1;
             } else {
                 x2 = aff_load_x<FIRST>(entries, pts, sl.i0 + 1);
