@@ -42,7 +42,8 @@ import numpy as np  # noqa: E402
 
 CANON_WINDOW = 16                      # canonical c = 16 => W = 16 bucket insertions / point
 LMAC_PER_MADD = 3000                   # canonical: 10 Fq multiplications x 300 LMAC
-EXEC_LMAC_PER_MADD = 6 * 300 + 2 * 234 + 444   # executed: 6 mul, 2 half-product squarings, 1 fused a*b-c*d (2 products, 1 reduction)
+EXEC_LMAC_PER_MADD = 6 * 300 + 2 * 234 + 444   # executed by the XYZZ kernel: 6 mul, 2 half-product squarings, 1 fused a*b-c*d (2 products, 1 reduction)
+EXEC_LMAC_PER_AFFINE_ADD = 5 * 300 + 234 + 60  # executed by the affine stage: prefix product, 1/d, running inverse, lambda, y3; lambda^2 as a half-product squaring; ~0.2 products of block trees
 CANON_LMAC_PER_POINT = 16 * LMAC_PER_MADD
 
 
@@ -260,7 +261,7 @@ def main() -> None:
     want_sha = golden_sha(args.log_n, Q)
     written = ctypes.c_uint64(0)
     STAGES = ("msm", "msm.sort", "msm.accumulate", "msm.accumulate_kernel", "msm.reduce", "poly", "total",
-              "msm.window_bits", "msm.windows", "msm.terms", "msm.entries", "msm.chunk", "msm.buckets", "msm.jobs")
+              "msm.window_bits", "msm.windows", "msm.terms", "msm.entries", "msm.chunk", "msm.buckets", "msm.jobs", "msm.affine")
 
     def check_proof(proof: bytes, what: str):
         if want_sha is not None and hashlib.sha256(proof).hexdigest() != want_sha:
@@ -616,10 +617,11 @@ def main() -> None:
         acc_ms = stage["msm.accumulate_kernel"]
         shard_terms = stage["msm.terms"]                       # terms device 0's launch processed
         canon_lmac = shard_terms * CANON_LMAC_PER_POINT
-        exec_lmac = stage["msm.entries"] * EXEC_LMAC_PER_MADD
+        affine = bool(stage.get("msm.affine"))
+        exec_lmac = stage["msm.entries"] * (EXEC_LMAC_PER_AFFINE_ADD if affine else EXEC_LMAC_PER_MADD)
         achieved = canon_lmac / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else 0.0
         traffic = None
-        if world == 1 and args.log_n == 16:
+        if world == 1 and args.log_n == 16 and not affine:
             # measured under ncu --set full on this configuration only (profiles/): not repeated where it was not profiled
             tpath = sorted([os.path.join(ROOT, "profiles", f) for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_accumulate_traffic.json")] or [""])[-1]
             if os.path.exists(tpath):
@@ -633,12 +635,15 @@ def main() -> None:
         except Exception:
             pass
         roofline = {
-            "bound": "imad", "kernel": "k_msm_accumulate_compact", "achieved": achieved, "peak": imad_peak / 1e12, "unit": "TLMAC/s",
+            "bound": "imad",
+            "kernel": "bucket stage in affine coordinates: k_aff_prefix + k_aff_inverses + k_aff_add per round, serial tail" if affine else "k_msm_accumulate_compact",
+            "achieved": achieved, "peak": imad_peak / 1e12, "unit": "TLMAC/s",
             "frac": achieved / (imad_peak / 1e12) if imad_peak else None, "traffic": traffic,
             "note": "integer-multiply roofline (SURVEY.md 8d) of ONE device's launch: achieved = canonical LMAC (terms of that launch x ceil(255/16) x 3000) "
                     "/ kernel time; peak = max of four register-only IMAD microbenchmarks measured in this run on one device (of measured)",
             "executed": {"tlmac_per_s": exec_lmac / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else 0.0,
                          "frac": (exec_lmac / (acc_ms * 1e-3)) / imad_peak if acc_ms > 0 and imad_peak else None,
+                         "lmac_per_insertion": EXEC_LMAC_PER_AFFINE_ADD if affine else EXEC_LMAC_PER_MADD,
                          "window_bits": stage["msm.window_bits"], "windows": stage["msm.windows"], "entries": stage["msm.entries"]},
             "kernel_ms": acc_ms, "msm_ms": stage["msm"], "kernel_share_of_step": acc_ms / ms_per_step if ms_per_step else None,
             "whole_msm_frac": (canon_lmac / (stage["msm"] * 1e-3)) / imad_peak if stage["msm"] > 0 and imad_peak else None,

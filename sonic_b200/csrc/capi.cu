@@ -611,7 +611,7 @@ int sonic_init(const int* devices, int ndev) {
             for (auto& e : cx.ev) SONIC_CUDA(cudaEventCreate(&e));
             for (auto& e : cx.ovl) SONIC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             cx.launches = 0;
-            if (const char* e = getenv("SONIC_ACC_MODE")) { int v = atoi(e); if (v >= 0 && v <= 2) cx.opt_acc_mode = v; }   // test / profiling hook
+            if (const char* e = getenv("SONIC_ACC_MODE")) { int v = atoi(e); if (v >= 0 && v <= 3) cx.opt_acc_mode = v; }   // test / profiling hook
             cx.ready = true;
         }
         R.ndev = ndev;
@@ -1599,7 +1599,7 @@ int sonic_set_option(const char* name, int64_t value) {
         if (value < 0 || value > 256) return fail(SONIC_ERR_INVALID_ARG, "reduce_k must be in [0, 256]");
         each([&](Ctx& cx) { cx.opt_reduce_k = (int)value; });
     } else if (!strcmp(name, "acc_mode")) {
-        if (value < 0 || value > 2) return fail(SONIC_ERR_INVALID_ARG, "acc_mode must be 0 (XYZZ in registers), 1 (XYZZ, operand file in shared memory) or 2 (affine, batched inversions)");
+        if (value < 0 || value > 3) return fail(SONIC_ERR_INVALID_ARG, "acc_mode must be 0 (XYZZ in registers), 1 (XYZZ, operand file in shared memory), 2 (affine, batched inversions) or 3 (automatic)");
         each([&](Ctx& cx) { cx.opt_acc_mode = (int)value; });
     } else if (!strcmp(name, "acc_blocks")) {
         if (value != 3) return fail(SONIC_ERR_INVALID_ARG, "acc_blocks is fixed at 3 in this build");
@@ -1610,6 +1610,12 @@ int sonic_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "aff_fused")) {
         if (value < 0 || value > 1) return fail(SONIC_ERR_INVALID_ARG, "aff_fused must be 0 or 1");
         each([&](Ctx& cx) { cx.opt_aff_fused = (int)value; });
+    } else if (!strcmp(name, "aff_m")) {
+        if (value != 0 && value != 8 && value != 16 && value != 32) return fail(SONIC_ERR_INVALID_ARG, "aff_m must be 0, 8, 16 or 32");
+        each([&](Ctx& cx) { cx.opt_aff_m = (int)value; });
+    } else if (!strcmp(name, "aff_tail")) {
+        if (value < 0 || value > 5) return fail(SONIC_ERR_INVALID_ARG, "aff_tail must be in [0, 5]");
+        each([&](Ctx& cx) { cx.opt_aff_tail = (int)value; });
     } else if (!strcmp(name, "overlap")) {
         if (value < 0 || value > 1) return fail(SONIC_ERR_INVALID_ARG, "overlap must be 0 or 1");
         each([&](Ctx& cx) { cx.opt_overlap = (int)value; });

@@ -119,10 +119,12 @@ struct Ctx {
     int opt_window_bits = 0;
     int opt_chunk = 0;
     int opt_aff_fused = 0;                                // affine accumulation: 0 prefix / inverses / add kernels per round, 1 one kernel per round with the inversion inside the block (measured 2x slower)
+    int opt_aff_m = 0;                                    // affine accumulation: slots per thread (0 = by round size; 8, 16, 32)
+    int opt_aff_tail = 4;                                 // affine accumulation: halvings left to the serial XYZZ tail
     int opt_heavy_mode = 1;                               // 1 one 128-thread block per heavy bucket (default), 0 by quads in two steps (measured: no gain at 8 GPUs, 0.27 -> 0.47 ms on one)
     int opt_overlap = 0;                                  // 1: two MSM batches per proof on two streams (tail of the first under the accumulation of the second); measured slower, off
     int opt_chunk_max = 0;                                // longest chunk the automatic rule may pick (0 = default)
-    int opt_acc_mode = 1;                                 // 0 straight-line mixed addition in registers, 1 compact (operand file in shared memory)
+    int opt_acc_mode = 3;                                 // 0 XYZZ, straight-line mixed addition in registers; 1 XYZZ compact (operand file in shared memory); 2 affine with batched inversions; 3 automatic (2 for >= 2^25 entries, else 1)
     bool opt_g2 = false;                                  // SRS.new also generates the G2 h-vectors
     int opt_reduce_mode = 0;                              // 0 automatic (quads of lanes while latency-bound, else thread per K buckets), 1 level by level, 2 thread per K buckets, 3 quads
     int opt_sort_mode = 1;                                // 0 thread per term + global atomics, 1 tiled counting sort (shared-memory histograms)

@@ -384,7 +384,14 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const u
     }
     mark(1);
 
-    const bool affine = cx.opt_acc_mode == 2;
+    // acc_mode 3 (automatic, the default): the affine stage with batched inversions for batches of at least 2^25 entries
+    // (a whole n = 2^16 proof, or half of it: 45.5 against 49.0 ms, a rank of two 25.1 against 26.3 ms), the XYZZ chunk kernel
+    // below that (its rounds cost ~0.2 ms each in small kernels: a rank of eight 8.7 against 7.8 ms)
+    // -- and only while the window tables are small (<= 8 GB): the affine stage gathers every input of its first round
+    // twice, which the L2 absorbs in part for the 2.8 GB tables of a proof but not for the 42 GB of a d = 2^23 SRS with
+    // 20-bit tables (2^22-point MSM: 23.1 against 22.0 ms, skewed scalars 14.6 against 10.8 ms)
+    const uint64_t table_bytes = (uint64_t)(tables.c > 0 ? tables.W : 1) * tables.stride * sizeof(G1Affine);
+    const bool affine = cx.opt_acc_mode == 2 || (cx.opt_acc_mode == 3 && total_max >= (1ull << 25) && tables.c > 0 && table_bytes <= (8ull << 30));
     const uint32_t chunks = affine ? 0u : div_up(total_max, p.L);
     G1XYZZ* buckets = ar.get<G1XYZZ>(p.GB);
     G1XYZZ* head = ar.get<G1XYZZ>(chunks ? chunks : 1);
@@ -397,7 +404,7 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const u
         for (int i = 0; i < M; ++i) mean = std::max(mean, (double)jobs[i].n * p.W / ((double)p.sets * p.B));
         launch_accumulate_affine(cx, total_max, entries, offsets, p.GB, d_points, buckets, mean);
     } else if (chunks) {
-        if (cx.opt_acc_mode == 1) launch_accumulate_compact(cx, chunks, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
+        if (cx.opt_acc_mode != 0) launch_accumulate_compact(cx, chunks, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
         else launch_accumulate_regs(cx, chunks, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
     }
     mark(5);
@@ -409,6 +416,7 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const u
         cx.timing_ms["msm.terms"] = n_tot;
         cx.timing_ms["msm.jobs"] = M;
         cx.timing_ms["msm.chunk"] = p.L;
+        cx.timing_ms["msm.affine"] = affine ? 1 : 0;
         cx.timing_ms["msm.buckets"] = p.GB;
         cx.msm_offsets_total = offsets + p.GB;
     } else {

@@ -15,6 +15,7 @@
 // proof 7.4 against 5.9 ms (nine rounds of small kernels).  The additions run at 60-70 % of the multiplier pipe
 // (barrier stalls of the block product tree, instruction-cache misses, dependent loads in front of every five
 // products); the denominator pass is bound by its gathers.  `acc_mode` therefore stays 1; DESIGN.md section 4.2.
+#include <algorithm>
 #include <cmath>
 
 #include "msm_acc.cuh"
@@ -22,11 +23,10 @@
 namespace sonic {
 
 constexpr int AF_T = 128;               // threads per block of the A / C kernels
-constexpr int AF_M = 32;                // output slots per thread
-constexpr int AF_SLOTS = AF_T * AF_M;   // slots per block = denominators per block total
+constexpr int AF_M_MAX = 32;            // output slots per thread: 32 / 16 / 8, by the size of the round (template parameter M)
 constexpr int AF_MAX_ROUNDS = 12;
 constexpr int AF_BT = 1024;             // threads of the single block of kernel B
-constexpr int AF_LEFT_SERIAL = 16;      // a bucket left with at most this many points after the last round is summed by one thread
+constexpr int AF_LEFT_SERIAL = 32;      // a bucket left with at most this many points after the last round is summed by one thread
 
 // ---- round bookkeeping -------------------------------------------------------------------------------------
 // cnt[b] points of bucket b start at base[b] in the round's input; the round leaves n = ceil(cnt / 2) of them.
@@ -143,14 +143,14 @@ SONIC_D int aff_kind(const uint32_t* __restrict__ entries, const G1Affine* __res
 }
 
 // ---- A: denominators and their running products -------------------------------------------------------------------
-template <bool FIRST>
+template <bool FIRST, int AF_M>
 __global__ void __launch_bounds__(AF_T, 4)
 k_aff_prefix(const uint32_t* __restrict__ entries, const G1Affine* __restrict__ pts, const uint32_t* __restrict__ wo,
              const uint32_t* __restrict__ base, const uint32_t* __restrict__ cnt, uint32_t GB, Fq* __restrict__ pre,
              Fq* __restrict__ block_tot) {
     __shared__ Fq tree[AF_T];
     const uint32_t total = wo[GB];
-    if (blockIdx.x * (uint32_t)AF_SLOTS >= total) return;   // the whole block is beyond the round's slots (uniform)
+    if (blockIdx.x * (uint32_t)(AF_T * AF_M) >= total) return;   // the whole block is beyond the round's slots (uniform)
     const uint32_t s0 = (blockIdx.x * AF_T + threadIdx.x) * AF_M;
     Fq run = Fq::one();
     if (s0 < total) {
@@ -180,11 +180,12 @@ k_aff_prefix(const uint32_t* __restrict__ entries, const G1Affine* __restrict__ 
 // thread t owns `per` consecutive totals: running products (kept in global scratch), a product tree over the thread
 // totals in shared memory, the Euclid inverse of the root, the tree walked back down, back-substitution.
 __global__ void __launch_bounds__(AF_BT)
-k_aff_inverses(const Fq* __restrict__ tot, const uint32_t* __restrict__ wo, uint32_t GB, Fq* __restrict__ scratch, Fq* __restrict__ inv) {
+k_aff_inverses(const Fq* __restrict__ tot, const uint32_t* __restrict__ wo, uint32_t GB, uint32_t slots_per_block, Fq* __restrict__ scratch,
+               Fq* __restrict__ inv) {
     extern __shared__ uint32_t af_smem_raw[];
     Fq* tree = reinterpret_cast<Fq*>(af_smem_raw);   // 2 * AF_BT nodes, node 1 = root, leaves at AF_BT + t
     const uint32_t total = wo[GB];
-    const uint32_t nb = (total + AF_SLOTS - 1) / AF_SLOTS;
+    const uint32_t nb = (total + slots_per_block - 1) / slots_per_block;
     if (nb == 0) return;
     const uint32_t per = (nb + AF_BT - 1) / AF_BT;
     const uint32_t i0 = threadIdx.x * per, i1 = i0 + per < nb ? i0 + per : nb;
@@ -222,14 +223,14 @@ k_aff_inverses(const Fq* __restrict__ tot, const uint32_t* __restrict__ wo, uint
 }
 
 // ---- C: 1/d per slot, the additions ---------------------------------------------------------------------------------------
-template <bool FIRST>
+template <bool FIRST, int AF_M>
 __global__ void __launch_bounds__(AF_T, 3)
 k_aff_add(const uint32_t* __restrict__ entries, const G1Affine* __restrict__ pts, const uint32_t* __restrict__ wo,
           const uint32_t* __restrict__ base, const uint32_t* __restrict__ cnt, uint32_t GB, const Fq* __restrict__ pre,
           const Fq* __restrict__ inv_tot, G1Affine* __restrict__ out, G1XYZZ* __restrict__ buckets) {
     __shared__ Fq tree[2 * AF_T];   // node 1 = root, leaves at AF_T + t
     const uint32_t total = wo[GB];
-    if (blockIdx.x * (uint32_t)AF_SLOTS >= total) return;
+    if (blockIdx.x * (uint32_t)(AF_T * AF_M) >= total) return;
     const uint32_t s0 = (blockIdx.x * AF_T + threadIdx.x) * AF_M;
     const uint32_t s1 = s0 >= total ? s0 : (total - s0 < (uint32_t)AF_M ? total : s0 + AF_M);   // this thread's slots [s0, s1)
     // 1 / (this thread's product): the block's product tree, walked down from the inverse of its root
@@ -484,6 +485,9 @@ void launch_accumulate_affine(Ctx& cx, uint64_t entries_max, const uint32_t* ent
     // rounds: enough for a bucket six standard deviations above the longest job's mean size
     int AF_ROUNDS = 4;
     while (AF_ROUNDS < AF_MAX_ROUNDS && (double)(1u << AF_ROUNDS) < max_mean_bucket + 6.0 * sqrt(max_mean_bucket) + 2.0) ++AF_ROUNDS;
+    // the last `aff_tail` halvings are left to the serial tail (k_aff_left_list: a thread sums the <= 2^aff_tail points a bucket
+    // still has with mixed XYZZ additions): the late rounds hold few additions each and cost their fixed ~0.2 ms anyway
+    AF_ROUNDS = std::max(1, AF_ROUNDS - cx.opt_aff_tail);
     // upper bounds of the work slots per round: every bucket halves, rounding up
     uint64_t smax[AF_MAX_ROUNDS];
     uint64_t prev = entries_max;
@@ -496,7 +500,7 @@ void launch_accumulate_affine(Ctx& cx, uint64_t entries_max, const uint32_t* ent
     uint32_t* wo[2] = {ar.get<uint32_t>((size_t)GB + 1), ar.get<uint32_t>((size_t)GB + 1)};
     G1Affine* buf[2] = {ar.get<G1Affine>(smax[0]), ar.get<G1Affine>(AF_ROUNDS > 1 ? smax[1] : 1)};
     Fq* pre = ar.get<Fq>(smax[0]);
-    const uint64_t nb_max = (smax[0] + AF_SLOTS - 1) / AF_SLOTS;
+    const uint64_t nb_max = (smax[0] + AF_T * 8 - 1) / (AF_T * 8);
     Fq* tot = ar.get<Fq>(nb_max);
     Fq* inv = ar.get<Fq>(nb_max);
     Fq* scratch = ar.get<Fq>(nb_max);
@@ -516,17 +520,21 @@ void launch_accumulate_affine(Ctx& cx, uint64_t entries_max, const uint32_t* ent
             else SONIC_LAUNCH(k_aff_fused<false>, fblocks, AF_T, AF_FSMEM, (const uint32_t*)nullptr, (const G1Affine*)buf[prv], wo[cur], base[cur], cnt[cur], GB, out, buckets);
             continue;
         }
-        const unsigned blocks = div_up(smax[r], AF_SLOTS);
-        if (r == 0) {
-            SONIC_LAUNCH(k_aff_prefix<true>, blocks, AF_T, 0, entries, points, wo[cur], base[cur], cnt[cur], GB, pre, tot);
-            SONIC_LAUNCH(k_aff_inverses, 1, AF_BT, b_smem, tot, wo[cur], GB, scratch, inv);
-            SONIC_LAUNCH(k_aff_add<true>, blocks, AF_T, 0, entries, points, wo[cur], base[cur], cnt[cur], GB, pre, inv, out, buckets);
-        } else {
-            const G1Affine* in = buf[prv];
-            SONIC_LAUNCH(k_aff_prefix<false>, blocks, AF_T, 0, (const uint32_t*)nullptr, in, wo[cur], base[cur], cnt[cur], GB, pre, tot);
-            SONIC_LAUNCH(k_aff_inverses, 1, AF_BT, b_smem, tot, wo[cur], GB, scratch, inv);
-            SONIC_LAUNCH(k_aff_add<false>, blocks, AF_T, 0, (const uint32_t*)nullptr, in, wo[cur], base[cur], cnt[cur], GB, pre, inv, out, buckets);
-        }
+        // slots per thread by the size of the round: long per-thread runs amortise the block's product tree (32 slots: the
+        // barrier stalls halve against 16), short ones keep the last wave of a small round short
+        const int m = cx.opt_aff_m > 0 ? cx.opt_aff_m : (smax[r] >= (8u << 20) ? 32 : smax[r] >= (2u << 20) ? 16 : 8);
+        const unsigned blocks = div_up(smax[r], (uint64_t)AF_T * m);
+        const uint32_t* e = r == 0 ? entries : nullptr;
+        const G1Affine* in = r == 0 ? points : buf[prv];
+#define AF_ROUND(FIRST, M)                                                                                                              \
+        do {                                                                                                                            \
+            SONIC_LAUNCH((k_aff_prefix<FIRST, M>), blocks, AF_T, 0, e, in, wo[cur], base[cur], cnt[cur], GB, pre, tot);                 \
+            SONIC_LAUNCH(k_aff_inverses, 1, AF_BT, b_smem, tot, wo[cur], GB, (uint32_t)(AF_T * M), scratch, inv);                       \
+            SONIC_LAUNCH((k_aff_add<FIRST, M>), blocks, AF_T, 0, e, in, wo[cur], base[cur], cnt[cur], GB, pre, inv, out, buckets);      \
+        } while (0)
+        if (r == 0) { if (m == 32) AF_ROUND(true, 32); else if (m == 16) AF_ROUND(true, 16); else AF_ROUND(true, 8); }
+        else { if (m == 32) AF_ROUND(false, 32); else if (m == 16) AF_ROUND(false, 16); else AF_ROUND(false, 8); }
+#undef AF_ROUND
     }
     // buckets that still hold more than one point after the last round
     const int last = (AF_ROUNDS - 1) & 1;
