@@ -1608,10 +1608,10 @@ int sonic_set_option(const char* name, int64_t value) {
         if (value < 0 || value > 4096) return fail(SONIC_ERR_INVALID_ARG, "chunk must be in [0, 4096]");
         each([&](Ctx& cx) { cx.opt_chunk = (int)value; });
     } else if (!strcmp(name, "aff_fused")) {
-        if (value < 0 || value > 1) return fail(SONIC_ERR_INVALID_ARG, "aff_fused must be 0 or 1");
+        if (value < 0 || value > 2) return fail(SONIC_ERR_INVALID_ARG, "aff_fused must be 0, 1 or 2");
         each([&](Ctx& cx) { cx.opt_aff_fused = (int)value; });
     } else if (!strcmp(name, "aff_m")) {
-        if (value != 0 && value != 8 && value != 16 && value != 32) return fail(SONIC_ERR_INVALID_ARG, "aff_m must be 0, 8, 16 or 32");
+        if (value != 0 && value != 8 && value != 16 && value != 32 && value != 64) return fail(SONIC_ERR_INVALID_ARG, "aff_m must be 0, 8, 16, 32 or 64");
         each([&](Ctx& cx) { cx.opt_aff_m = (int)value; });
     } else if (!strcmp(name, "aff_tail")) {
         if (value < 0 || value > 5) return fail(SONIC_ERR_INVALID_ARG, "aff_tail must be in [0, 5]");

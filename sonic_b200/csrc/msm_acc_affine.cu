@@ -25,7 +25,7 @@ namespace sonic {
 constexpr int AF_T = 128;               // threads per block of the A / C kernels
 constexpr int AF_M_MAX = 32;            // output slots per thread: 32 / 16 / 8, by the size of the round (template parameter M)
 constexpr int AF_MAX_ROUNDS = 12;
-constexpr int AF_BT = 1024;             // threads of the single block of kernel B
+constexpr int AF_BT = 256;              // threads per block of kernel B
 constexpr int AF_LEFT_SERIAL = 32;      // a bucket left with at most this many points after the last round is summed by one thread
 
 // ---- round bookkeeping -------------------------------------------------------------------------------------
@@ -176,19 +176,23 @@ k_aff_prefix(const uint32_t* __restrict__ entries, const G1Affine* __restrict__ 
     if (threadIdx.x == 0) block_tot[blockIdx.x] = tree[0];
 }
 
-// ---- B: the inverses of all block totals from ONE inversion ---------------------------------------------------------
-// thread t owns `per` consecutive totals: running products (kept in global scratch), a product tree over the thread
-// totals in shared memory, the Euclid inverse of the root, the tree walked back down, back-substitution.
+// ---- B: the inverses of all block totals ----------------------------------------------------------------------------------------
+// Every block of AF_BT threads takes an equal share of the totals and pays one Euclid inversion for it: thread t owns `per`
+// consecutive totals: running products (kept in global scratch), a product tree over the thread totals in shared memory,
+// the inverse of the root, the tree walked back down, back-substitution.  (One block for everything spent 0.13-0.33 ms
+// per round on a single SM -- fifteen serial products per thread in the first round; the launcher now gives a block at
+// most AF_BT totals, so `per` is 1.)
 __global__ void __launch_bounds__(AF_BT)
 k_aff_inverses(const Fq* __restrict__ tot, const uint32_t* __restrict__ wo, uint32_t GB, uint32_t slots_per_block, Fq* __restrict__ scratch,
                Fq* __restrict__ inv) {
-    extern __shared__ uint32_t af_smem_raw[];
-    Fq* tree = reinterpret_cast<Fq*>(af_smem_raw);   // 2 * AF_BT nodes, node 1 = root, leaves at AF_BT + t
+    __shared__ Fq tree[2 * AF_BT];   // node 1 = root, leaves at AF_BT + t
     const uint32_t total = wo[GB];
     const uint32_t nb = (total + slots_per_block - 1) / slots_per_block;
-    if (nb == 0) return;
-    const uint32_t per = (nb + AF_BT - 1) / AF_BT;
-    const uint32_t i0 = threadIdx.x * per, i1 = i0 + per < nb ? i0 + per : nb;
+    const uint32_t share = (nb + gridDim.x - 1) / gridDim.x;
+    const uint32_t lo = blockIdx.x * share, hi = lo + share < nb ? lo + share : nb;
+    if (lo >= hi) return;
+    const uint32_t per = (hi - lo + AF_BT - 1) / AF_BT;
+    const uint32_t i0 = lo + threadIdx.x * per < hi ? lo + threadIdx.x * per : hi, i1 = i0 + per < hi ? i0 + per : hi;
     Fq run = Fq::one();
     for (uint32_t i = i0; i < i1; ++i) {
         run = fp_mul(run, tot[i]);
@@ -431,6 +435,102 @@ k_aff_fused(const uint32_t* __restrict__ entries, const G1Affine* __restrict__ p
     }
 }
 
+// ---- A + B + C in one kernel, running products in global memory (option `aff_fused` = 2) ------------------------------------
+// The shared-memory form above can hold 8 slots per thread, and a block then waits on its barriers (fourteen tree levels
+// and the Euclid inverse of the root, ~60 us) for a third of its life.  With the running products in `pre` (written and
+// re-read by the same thread a few hundred microseconds apart) a thread takes M = 16 or 32 slots, the wait is a tenth of
+// the block's life and the other three blocks of the SM cover it; the separate denominator pass over the inputs, kernel
+// B and its single-SM serial section are gone.
+template <bool FIRST, int AF_M>
+__global__ void __launch_bounds__(AF_T, 4)
+k_aff_round(const uint32_t* __restrict__ entries, const G1Affine* __restrict__ pts, const uint32_t* __restrict__ wo,
+            const uint32_t* __restrict__ base, const uint32_t* __restrict__ cnt, uint32_t GB, Fq* __restrict__ pre,
+            G1Affine* __restrict__ out, G1XYZZ* __restrict__ buckets) {
+    __shared__ Fq tree[2 * AF_T];   // node 1 = root, leaves at AF_T + t
+    const uint32_t total = wo[GB];
+    if (blockIdx.x * (uint32_t)(AF_T * AF_M) >= total) return;
+    const uint32_t s0 = (blockIdx.x * AF_T + threadIdx.x) * AF_M;
+    const uint32_t s1 = s0 >= total ? s0 : (total - s0 < (uint32_t)AF_M ? total : s0 + AF_M);   // this thread's slots [s0, s1)
+    uint32_t bs[AF_M];
+    {
+        Fq run = Fq::one();
+        if (s1 > s0) {
+            uint32_t b = aff_find_bucket(wo, GB, s0);
+            for (int j = 0; j < AF_M; ++j) {
+                const uint32_t s = s0 + j;
+                if (s >= s1) break;
+                const AffSlot sl = aff_slot(s, b, wo, base, cnt, GB);
+                bs[j] = b;
+                const Fq x1 = aff_load_x<FIRST>(entries, pts, sl.i0);
+                Fq d;
+                aff_kind<FIRST>(entries, pts, sl, x1, d);
+                run = fp_mul(run, d);
+                pre[s] = run;
+            }
+        }
+        tree[AF_T + threadIdx.x] = run;
+    }
+    __syncthreads();
+    for (int w = AF_T / 2; w >= 1; w >>= 1) {
+        if ((int)threadIdx.x < w) {
+            const int i = w + threadIdx.x;
+            tree[i] = fp_mul(tree[2 * i], tree[2 * i + 1]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tree[1] = fp_inv_euclid(tree[1]);
+    __syncthreads();
+    for (int w = 1; w <= AF_T / 2; w <<= 1) {
+        if ((int)threadIdx.x < w) {
+            const int i = w + threadIdx.x;
+            const Fq l = tree[2 * i], r = tree[2 * i + 1], iv = tree[i];
+            tree[2 * i] = fp_mul(iv, r);
+            tree[2 * i + 1] = fp_mul(iv, l);
+        }
+        __syncthreads();
+    }
+    if (s1 <= s0) return;
+    Fq inv_run = tree[AF_T + threadIdx.x];
+    for (int j = AF_M - 1; j >= 0; --j) {
+        const uint32_t s = s0 + j;
+        if (s >= s1) continue;
+        uint32_t b = bs[j];
+        const AffSlot sl = aff_slot(s, b, wo, base, cnt, GB);
+        const Fq x1 = aff_load_x<FIRST>(entries, pts, sl.i0);
+        Fq d;
+        const int kind = aff_kind<FIRST>(entries, pts, sl, x1, d);
+        const Fq prev = j > 0 ? pre[s - 1] : Fq::one();
+        const Fq inv_d = fp_mul(inv_run, prev);
+        inv_run = fp_mul(inv_run, d);
+        G1Affine r;
+        if (kind == AK_COPY) {
+            r.x = x1;
+            r.y = aff_load_y<FIRST>(entries, pts, sl.i0);
+        } else if (kind == AK_TAKE2) {
+            r.x = aff_load_x<FIRST>(entries, pts, sl.i0 + 1);
+            r.y = aff_load_y<FIRST>(entries, pts, sl.i0 + 1);
+        } else if (kind == AK_INF) {
+            r = G1Affine::inf();
+        } else {
+            const Fq y1 = aff_load_y<FIRST>(entries, pts, sl.i0);
+            Fq lambda, x2;
+            if (kind == AK_DBL) {
+                const Fq xx = fp_sqr(x1);
+                lambda = fp_mul(fp_add(fp_dbl(xx), xx), inv_d);   // 3 x^2 / 2y
+                x2 = x1;
+            } else {
+                x2 = aff_load_x<FIRST>(entries, pts, sl.i0 + 1);
+                const Fq y2 = aff_load_y<FIRST>(entries, pts, sl.i0 + 1);
+                lambda = fp_mul(fp_sub(y2, y1), inv_d);
+            }
+            r.x = fp_sub(fp_sub(fp_sqr(lambda), x1), x2);
+            r.y = fp_sub(fp_mul(lambda, fp_sub(x1, r.x)), y1);
+        }
+        if (sl.last) store_xyzz(buckets + sl.b, G1XYZZ::from_affine(r));
+        else out[s] = r;
+    }
+}
+
 // ---- what is left of buckets longer than 2^R entries -----------------------------------------------------------------------
 // a few points: the thread that finds them sums them; many (a 65 536-entry bucket still has hundreds): one block each
 __global__ void __launch_bounds__(128) k_aff_left_list(const uint32_t* __restrict__ cnt_prev, const uint32_t* __restrict__ wo_prev,
@@ -504,8 +604,6 @@ void launch_accumulate_affine(Ctx& cx, uint64_t entries_max, const uint32_t* ent
     Fq* tot = ar.get<Fq>(nb_max);
     Fq* inv = ar.get<Fq>(nb_max);
     Fq* scratch = ar.get<Fq>(nb_max);
-    const size_t b_smem = 2 * (size_t)AF_BT * sizeof(Fq);
-    SONIC_CUDA(cudaFuncSetAttribute(k_aff_inverses, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b_smem));
     SONIC_CUDA(cudaFuncSetAttribute(k_aff_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AF_FSMEM));
     SONIC_CUDA(cudaFuncSetAttribute(k_aff_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AF_FSMEM));
     for (int r = 0; r < AF_ROUNDS; ++r) {
@@ -514,7 +612,7 @@ void launch_accumulate_affine(Ctx& cx, uint64_t entries_max, const uint32_t* ent
         else SONIC_LAUNCH(k_aff_prepare_next, div_up((uint64_t)GB + 1, 256), 256, 0, cnt[prv], wo[prv], GB, base[cur], cnt[cur], wo[cur]);
         exclusive_scan_u32(ar, wo[cur], wo[cur], GB + 1);
         G1Affine* out = buf[cur];
-        if (cx.opt_aff_fused) {
+        if (cx.opt_aff_fused == 1) {
             const unsigned fblocks = div_up(smax[r], AF_FSLOTS);
             if (r == 0) SONIC_LAUNCH(k_aff_fused<true>, fblocks, AF_T, AF_FSMEM, entries, points, wo[cur], base[cur], cnt[cur], GB, out, buckets);
             else SONIC_LAUNCH(k_aff_fused<false>, fblocks, AF_T, AF_FSMEM, (const uint32_t*)nullptr, (const G1Affine*)buf[prv], wo[cur], base[cur], cnt[cur], GB, out, buckets);
@@ -522,14 +620,28 @@ void launch_accumulate_affine(Ctx& cx, uint64_t entries_max, const uint32_t* ent
         }
         // slots per thread by the size of the round: long per-thread runs amortise the block's product tree (32 slots: the
         // barrier stalls halve against 16), short ones keep the last wave of a small round short
-        const int m = cx.opt_aff_m > 0 ? cx.opt_aff_m : (smax[r] >= (8u << 20) ? 32 : smax[r] >= (2u << 20) ? 16 : 8);
+        const int ladder = smax[r] >= (8u << 20) ? 32 : smax[r] >= (2u << 20) ? 16 : 8;
+        int m = cx.opt_aff_m > 0 ? cx.opt_aff_m : ladder;
+        if (m == 64) m = cx.opt_aff_fused == 2 && smax[r] >= (16u << 20) ? 64 : ladder;   // 64 slots: the one-kernel round only, large rounds only
         const unsigned blocks = div_up(smax[r], (uint64_t)AF_T * m);
         const uint32_t* e = r == 0 ? entries : nullptr;
         const G1Affine* in = r == 0 ? points : buf[prv];
+        if (cx.opt_aff_fused == 2) {
+#define AF_FROUND(FIRST, M) SONIC_LAUNCH((k_aff_round<FIRST, M>), blocks, AF_T, 0, e, in, wo[cur], base[cur], cnt[cur], GB, pre, out, buckets)
+            if (m == 64) {
+                const unsigned blocks64 = div_up(smax[r], (uint64_t)AF_T * 64);
+                if (r == 0) SONIC_LAUNCH((k_aff_round<true, 64>), blocks64, AF_T, 0, e, in, wo[cur], base[cur], cnt[cur], GB, pre, out, buckets);
+                else SONIC_LAUNCH((k_aff_round<false, 64>), blocks64, AF_T, 0, e, in, wo[cur], base[cur], cnt[cur], GB, pre, out, buckets);
+            } else if (r == 0) { if (m == 32) AF_FROUND(true, 32); else if (m == 16) AF_FROUND(true, 16); else AF_FROUND(true, 8); }
+            else { if (m == 32) AF_FROUND(false, 32); else if (m == 16) AF_FROUND(false, 16); else AF_FROUND(false, 8); }
+#undef AF_FROUND
+            continue;
+        }
+        const unsigned b_blocks = std::max(1u, std::min((unsigned)cx.sm_count, (unsigned)div_up((uint64_t)blocks, (uint64_t)AF_BT)));
 #define AF_ROUND(FIRST, M)                                                                                                              \
         do {                                                                                                                            \
             SONIC_LAUNCH((k_aff_prefix<FIRST, M>), blocks, AF_T, 0, e, in, wo[cur], base[cur], cnt[cur], GB, pre, tot);                 \
-            SONIC_LAUNCH(k_aff_inverses, 1, AF_BT, b_smem, tot, wo[cur], GB, (uint32_t)(AF_T * M), scratch, inv);                       \
+            SONIC_LAUNCH(k_aff_inverses, b_blocks, AF_BT, 0, tot, wo[cur], GB, (uint32_t)(AF_T * M), scratch, inv);                       \
             SONIC_LAUNCH((k_aff_add<FIRST, M>), blocks, AF_T, 0, e, in, wo[cur], base[cur], cnt[cur], GB, pre, inv, out, buckets);      \
         } while (0)
         if (r == 0) { if (m == 32) AF_ROUND(true, 32); else if (m == 16) AF_ROUND(true, 16); else AF_ROUND(true, 8); }
