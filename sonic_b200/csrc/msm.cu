@@ -384,14 +384,22 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const u
     }
     mark(1);
 
-    // acc_mode 3 (automatic, the default): the affine stage with batched inversions for batches of at least 2^25 entries
-    // (a whole n = 2^16 proof, or half of it: 45.5 against 49.0 ms, a rank of two 25.1 against 26.3 ms), the XYZZ chunk kernel
-    // below that (its rounds cost ~0.2 ms each in small kernels: a rank of eight 8.7 against 7.8 ms)
-    // -- and only while the window tables are small (<= 8 GB): the affine stage gathers every input of its first round
-    // twice, which the L2 absorbs in part for the 2.8 GB tables of a proof but not for the 42 GB of a d = 2^23 SRS with
-    // 20-bit tables (2^22-point MSM: 23.1 against 22.0 ms, skewed scalars 14.6 against 10.8 ms)
-    const uint64_t table_bytes = (uint64_t)(tables.c > 0 ? tables.W : 1) * tables.stride * sizeof(G1Affine);
-    const bool affine = cx.opt_acc_mode == 2 || (cx.opt_acc_mode == 3 && total_max >= (1ull << 25) && tables.c > 0 && table_bytes <= (8ull << 30));
+    // acc_mode 3 (automatic, the default): the affine stage with batched inversions for batches of at least ~2^24.3 entries
+    // (a whole n = 2^16 proof 43.4 against 49.0 ms, a rank of four 13.6 against 14.1 ms, a 2^24-point MSM 75.4 against
+    // 81.4 ms), the XYZZ chunk kernel below that (the rounds cost ~0.1 ms each in small kernels and barrier waits: a rank
+    // of eight 8.3 against 8.0 ms, a 2^20-point MSM 7.5 against 6.9 ms).  What counts are the entries that exist -- zero
+    // digits make none, and half of the scalars of the skewed sweep rows are zero -- so when the upper bound passes the
+    // threshold the actual count is read back (4 bytes; the host has to wait for the sort, ~20 us of idle GPU).
+    constexpr uint64_t AFFINE_MIN_ENTRIES = 5ull << 22;
+    uint64_t entries_bound = total_max;
+    bool affine = cx.opt_acc_mode == 2;
+    if (cx.opt_acc_mode == 3 && tables.c > 0 && total_max >= AFFINE_MIN_ENTRIES) {
+        uint32_t actual = 0;
+        SONIC_CUDA(cudaMemcpyAsync(&actual, offsets + p.GB, 4, cudaMemcpyDeviceToHost, st));
+        SONIC_CUDA(cudaStreamSynchronize(st));
+        affine = actual >= AFFINE_MIN_ENTRIES;
+        if (affine) entries_bound = actual;
+    }
     const uint32_t chunks = affine ? 0u : div_up(total_max, p.L);
     G1XYZZ* buckets = ar.get<G1XYZZ>(p.GB);
     G1XYZZ* head = ar.get<G1XYZZ>(chunks ? chunks : 1);
@@ -402,7 +410,7 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const u
         // mean entries per bucket of the longest job: its W digits land in `sets` bucket sets of B buckets
         double mean = 1.0;
         for (int i = 0; i < M; ++i) mean = std::max(mean, (double)jobs[i].n * p.W / ((double)p.sets * p.B));
-        launch_accumulate_affine(cx, total_max, entries, offsets, p.GB, d_points, buckets, mean);
+        launch_accumulate_affine(cx, entries_bound, entries, offsets, p.GB, d_points, buckets, mean);
     } else if (chunks) {
         if (cx.opt_acc_mode != 0) launch_accumulate_compact(cx, chunks, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);
         else launch_accumulate_regs(cx, chunks, entries, offsets, p.GB, p.L, d_points, buckets, head, tail);

@@ -115,13 +115,9 @@ SONIC_D Fq aff_load_y(const uint32_t* __restrict__ entries, const G1Affine* __re
     return y;
 }
 
-// pull the point behind input i towards L2 (the gathers of the first round are DRAM-latency bound otherwise)
-template <bool FIRST>
-SONIC_D void aff_prefetch(const uint32_t* __restrict__ entries, const G1Affine* __restrict__ pts, uint32_t i, bool whole) {
-    const G1Affine* p = FIRST ? pts + (entries[i] & 0x7fffffffu) : pts + i;
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    if (whole) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p) + 64));
-}
+// (No software prefetch: `prefetch.global.L2` of a slot's gathers, whether in a pass in front of the additions or one to
+// eight slots ahead inside the loop, cost 0.8-1.1 ms per n = 2^16 proof -- the stage is bound by its products, not by
+// the latency of its loads.)
 
 // What a slot does, and the denominator it contributes to the batch (1 when nothing is inverted).  A point of G1
 // with x = 0 does not exist ((0, +-2) has order 3), so x == 0 identifies the infinity marker (0,0).
@@ -272,11 +268,6 @@ k_aff_add(const uint32_t* __restrict__ entries, const G1Affine* __restrict__ pts
                 if (s >= wo[b + 1]) b = aff_find_bucket(wo, GB, s);
             }
             bs[j] = b;
-            if (FIRST) {
-                const uint32_t local = s - wo[b], k = cnt[b], i0 = base[b] + 2 * local;
-                aff_prefetch<FIRST>(entries, pts, i0, true);
-                if (2 * local + 1 < k) aff_prefetch<FIRST>(entries, pts, i0 + 1, true);
-            }
         }
     }
     for (int j = AF_M - 1; j >= 0; --j) {
@@ -620,9 +611,7 @@ void launch_accumulate_affine(Ctx& cx, uint64_t entries_max, const uint32_t* ent
         }
         // slots per thread by the size of the round: long per-thread runs amortise the block's product tree (32 slots: the
         // barrier stalls halve against 16), short ones keep the last wave of a small round short
-        const int ladder = smax[r] >= (8u << 20) ? 32 : smax[r] >= (2u << 20) ? 16 : 8;
-        int m = cx.opt_aff_m > 0 ? cx.opt_aff_m : ladder;
-        if (m == 64) m = cx.opt_aff_fused == 2 && smax[r] >= (16u << 20) ? 64 : ladder;   // 64 slots: the one-kernel round only, large rounds only
+        const int m = cx.opt_aff_m > 0 ? cx.opt_aff_m : smax[r] >= (16u << 20) ? 64 : smax[r] >= (8u << 20) ? 32 : smax[r] >= (2u << 20) ? 16 : 8;
         const unsigned blocks = div_up(smax[r], (uint64_t)AF_T * m);
         const uint32_t* e = r == 0 ? entries : nullptr;
         const G1Affine* in = r == 0 ? points : buf[prv];
@@ -644,8 +633,8 @@ void launch_accumulate_affine(Ctx& cx, uint64_t entries_max, const uint32_t* ent
             SONIC_LAUNCH(k_aff_inverses, b_blocks, AF_BT, 0, tot, wo[cur], GB, (uint32_t)(AF_T * M), scratch, inv);                       \
             SONIC_LAUNCH((k_aff_add<FIRST, M>), blocks, AF_T, 0, e, in, wo[cur], base[cur], cnt[cur], GB, pre, inv, out, buckets);      \
         } while (0)
-        if (r == 0) { if (m == 32) AF_ROUND(true, 32); else if (m == 16) AF_ROUND(true, 16); else AF_ROUND(true, 8); }
-        else { if (m == 32) AF_ROUND(false, 32); else if (m == 16) AF_ROUND(false, 16); else AF_ROUND(false, 8); }
+        if (r == 0) { if (m == 64) AF_ROUND(true, 64); else if (m == 32) AF_ROUND(true, 32); else if (m == 16) AF_ROUND(true, 16); else AF_ROUND(true, 8); }
+        else { if (m == 64) AF_ROUND(false, 64); else if (m == 32) AF_ROUND(false, 32); else if (m == 16) AF_ROUND(false, 16); else AF_ROUND(false, 8); }
 #undef AF_ROUND
     }
     // buckets that still hold more than one point after the last round

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Standalone MSMs 2^20..2^24 (uniform and skewed scalars) per accumulation mode: acc_mode 1 (XYZZ) against 3 (automatic)."""
+"""Standalone MSMs 2^20..2^24 (uniform and skewed scalars) per accumulation mode: acc_mode 1 (XYZZ) against 3 (automatic) or the mode given as second argument."""
 import ctypes
 import os
 import sys
@@ -11,6 +11,7 @@ import sonic_b200 as sb  # noqa: E402
 from sonic_b200 import capi, synth  # noqa: E402
 
 top = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+other = int(sys.argv[2]) if len(sys.argv) > 2 else 3   # the mode compared with XYZZ: 3 automatic, 2 affine always
 sb.init(0)
 L = capi.lib()
 x, alpha = synth.trapdoor()
@@ -28,7 +29,7 @@ for logn in (20, 22, top):
         capi.check(L.sonic_dev_upload(dsc, sc.ctypes.data, sc.nbytes))
         o48 = ctypes.create_string_buffer(48)
         res, pts = {}, {}
-        for mode in (1, 3):
+        for mode in (1, other):
             sb.set_option("acc_mode", mode)
             best = None
             for _ in range(3):
@@ -37,6 +38,6 @@ for logn in (20, 22, top):
                 if best is None or tm["msm"] < best["msm"]:
                     best = tm
             res[mode], pts[mode] = best, o48.raw
-        assert pts[1] == pts[3]
-        print(logn, kind, "xyzz", res[1], "auto", res[3], flush=True)
+        assert pts[1] == pts[other]
+        print(logn, kind, "xyzz", res[1], "mode %d" % other, res[other], flush=True)
         capi.check(L.sonic_dev_free(dsc))
