@@ -640,7 +640,9 @@ def main() -> None:
             "achieved": achieved, "peak": imad_peak / 1e12, "unit": "TLMAC/s",
             "frac": achieved / (imad_peak / 1e12) if imad_peak else None, "traffic": traffic,
             "note": "integer-multiply roofline (SURVEY.md 8d) of ONE device's launch: achieved = canonical LMAC (terms of that launch x ceil(255/16) x 3000) "
-                    "/ kernel time; peak = max of four register-only IMAD microbenchmarks measured in this run on one device (of measured)",
+                    "/ kernel time; peak = max of four register-only IMAD microbenchmarks measured in this run on one device (of measured)"
+                    + ("; frac can pass 1 here: the affine stage with batched inversions executes ~1 794 LMAC per insertion, fewer than the 3 000 "
+                       "of the canonical mixed addition the algorithmic figure is defined on -- `executed.frac` is the multiplier-pipe utilisation" if affine else ""),
             "executed": {"tlmac_per_s": exec_lmac / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else 0.0,
                          "frac": (exec_lmac / (acc_ms * 1e-3)) / imad_peak if acc_ms > 0 and imad_peak else None,
                          "lmac_per_insertion": EXEC_LMAC_PER_AFFINE_ADD if affine else EXEC_LMAC_PER_MADD,
