@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Turns the ncu artefacts brought back in gpurun_out/ into the tracked summaries under profiles/.
 
-  python tools/summarize_profiles.py <tag> <launches.csv> <kernel.ncu-rep> [first_launch_id_of_last_proof]
+  python tools/summarize_profiles.py <tag> <launches.csv> <kernel.ncu-rep | -> [first_launch_id_of_last_proof]
 """
 import collections
 import csv
@@ -54,6 +54,9 @@ md = [f"# {tag}: ncu launch list (`--metrics gpu__time_duration.sum --clock-cont
       f"## SRS.new + circuit load: {len(setup)} launches, {tot_s:.2f} ms summed", "", tab_s, ""]
 open(os.path.join(out_dir, f"{tag}_launches.md"), "w").write("\n".join(md))
 
+if rep == "-":   # launch list only
+    print("wrote", f"{tag}_launches.md", "proof launches", len(proof), "summed ms", round(tot_p, 2))
+    sys.exit(0)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(raw.splitlines()))
 h, u, v = rr[0], rr[1], rr[2]
