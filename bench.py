@@ -621,9 +621,11 @@ def main() -> None:
         exec_lmac = stage["msm.entries"] * (EXEC_LMAC_PER_AFFINE_ADD if affine else EXEC_LMAC_PER_MADD)
         achieved = canon_lmac / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else 0.0
         traffic = None
-        if world == 1 and args.log_n == 16 and not affine:
-            # measured under ncu --set full on this configuration only (profiles/): not repeated where it was not profiled
-            tpath = sorted([os.path.join(ROOT, "profiles", f) for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_accumulate_traffic.json")] or [""])[-1]
+        if world == 1 and args.log_n == 16:
+            # measured under ncu on this configuration only (profiles/): not repeated where it was not profiled.  Affine mode:
+            # the DRAM bytes of every kernel of the bucket stage of one proof (tools/ncu_affine_stage.sh)
+            suffix = "_affine_traffic.json" if affine else "_accumulate_traffic.json"
+            tpath = sorted([os.path.join(ROOT, "profiles", f) for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith(suffix)] or [""])[-1]
             if os.path.exists(tpath):
                 try:
                     traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
