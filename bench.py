@@ -464,9 +464,11 @@ def main() -> None:
                     # this rank's launch really inserted x the executed IMAD.WIDE per mixed addition; both against N x peak
                     entries = sb.last_timing_ms("msm.entries")
                     acc_ms = sb.last_timing_ms("msm.accumulate_kernel")
+                    row_affine = bool(sb.last_timing_ms("msm.affine"))
                     sweep.append({"log2_n": logn, "scalars": kind, "ms": ms, "mpoints_per_s": N / (ms * 1e-3) / 1e6,
                                   "frac_of_imad_peak": N * CANON_LMAC_PER_POINT / (ms * 1e-3) / (imad_peak * world),
-                                  "executed_frac_of_imad_peak": entries * world * EXEC_LMAC_PER_MADD / (ms * 1e-3) / (imad_peak * world),
+                                  "executed_frac_of_imad_peak": entries * world * (EXEC_LMAC_PER_AFFINE_ADD if row_affine else EXEC_LMAC_PER_MADD) / (ms * 1e-3) / (imad_peak * world),
+                                  "bucket_stage": "affine" if row_affine else "xyzz",
                                   "accumulate_kernel_ms_rank0": acc_ms, "entries_rank0": entries,
                                   "stages_ms_rank0": {k: sb.last_timing_ms(k) for k in ("msm.sort", "msm.accumulate", "msm.reduce")},
                                   "window_bits": sb.last_timing_ms("msm.window_bits"), "precomputed_tables": bool(sb.last_timing_ms("msm.precomputed"))})

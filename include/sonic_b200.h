@@ -252,13 +252,20 @@ int sonic_pcv_fold(uint64_t k, const uint8_t* F48, const uint8_t* W48, const uin
  * "shard_min_terms": a standalone MSM is cut across the devices when it has at least this many terms per device (default 2^17);
  * "g2" (0/1): SRS.new also generates the G2 vectors; "sort_mode" (0: thread per term with global
  * atomics, 1: tiled counting sort with shared-memory histograms [default], 2..64: tiled with that
- * many tiles per SM), "acc_mode", "acc_blocks", "reduce_mode", "reduce_k": kernel tuning knobs
- *  */
+ * many tiles per SM);
+ * "acc_mode": the bucket stage -- 3 (default) automatic: pairwise rounds in affine coordinates with batched inversions
+ * when the batch has at least 5*2^22 bucket entries, the XYZZ chunk kernel below; 2 affine always; 1 XYZZ, operands in
+ * shared memory; 0 XYZZ, operands in registers.  Every mode returns the same bytes.  "aff_tail" (0..5, default 4): the
+ * last halvings of a bucket left to a serial tail; "aff_m" (0 automatic | 8 | 16 | 32 | 64): output slots per thread
+ * of a round; "aff_fused" (0 | 1 | 2): one kernel per round with the inversion inside the block (measured slower);
+ * "acc_blocks", "chunk_max", "reduce_mode" (0 automatic, 1 level by level, 2 thread per K buckets, 3 quads of lanes),
+ * "reduce_k", "heavy_mode", "overlap": kernel tuning knobs */
 int sonic_set_option(const char* name, int64_t value);
 /* device time in milliseconds of the kernels of the last call, by stage name; returns 0
  * if unknown.  Stages: "msm", "msm.sort", "msm.accumulate", "msm.reduce", "msm.accumulate_kernel", "poly", "total";
  * the same call also reports counters of the last MSM batch: "msm.window_bits", "msm.windows",
- * "msm.terms", "msm.entries", "msm.jobs", "msm.chunk", "msm.buckets", "msm.sort_tiles" */
+ * "msm.terms", "msm.entries", "msm.jobs", "msm.chunk", "msm.buckets", "msm.sort_tiles", "msm.affine" (1 when the
+ * bucket stage ran in affine coordinates) */
 double sonic_last_timing_ms(const char* stage);
 /* the same for device `slot` of the sonic_init list (each device times its own share of a call) */
 double sonic_last_timing_ms_dev(int slot, const char* stage);

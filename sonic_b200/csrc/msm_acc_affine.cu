@@ -1,20 +1,25 @@
-// Bucket accumulation in affine coordinates with batched inversions (`acc_mode=2`).
+// Bucket accumulation in affine coordinates with batched inversions (`acc_mode` 2; chosen by the automatic mode 3 for
+// batches of at least 5 * 2^22 entries -- msm.cu).
 //
 // The XYZZ kernels spend ~9 multiplications on every insertion (8M + 2S; 2 712 IMAD.WIDE executed).  An
 // affine addition needs 1/(x2 - x1) and then only 3 (lambda, lambda^2, y3); with Montgomery's trick the
-// inversion of MANY independent denominators costs 3 multiplications each plus one real inversion for the
+// inversion of MANY independent denominators costs 3 multiplications each plus a few real inversions for the
 // lot.  Independent additions are what a pairwise tree reduction of the buckets offers: round r adds the
-// entries of every bucket two by two (all pairs of all buckets at once), halving every bucket, until a
-// bucket is down to one point.  ~6 multiplications per insertion instead of ~9, no chunk head/tail
-// pieces, no fix-up stage -- for ~0.5 KB of HBM traffic per insertion (the intermediate points and the
-// prefix products live in global memory; 60 GB per n = 2^16 proof).
+// entries of every bucket two by two (all pairs of all buckets at once), halving every bucket.  5.8
+// multiplications (1 794 IMAD.WIDE) per insertion, no chunk head/tail pieces, no fix-up stage -- for ~0.7 KB of
+// HBM traffic per insertion (the intermediate points and the running products live in global memory; 87 GB per
+// n = 2^16 proof, 2.3 TB/s on average: not the bound).
 //
-// STATUS: correct (every parity test, the golden proofs and the x = 1 trapdoor pass with SONIC_ACC_MODE=2) and about as
-// fast as the XYZZ kernel on a B200 (profiles/r02n_affine_vs_xyzz.json, r02n_affine_ncu.md): prove() at n = 2^16 47.3 ms
-// against 48.8 ms (it needs no fix-up stage), the 2^24-point MSM 82.8 against 81.6 ms, one rank of an 8-way sharded
-// proof 7.4 against 5.9 ms (nine rounds of small kernels).  The additions run at 60-70 % of the multiplier pipe
-// (barrier stalls of the block product tree, instruction-cache misses, dependent loads in front of every five
-// products); the denominator pass is bound by its gathers.  `acc_mode` therefore stays 1; DESIGN.md section 4.2.
+// Per round: A (k_aff_prefix) denominators and their per-thread running products, one product per block;
+// B (k_aff_inverses) the inverses of the block products, 256 per block of B and one Euclid inverse each;
+// C (k_aff_add) the block's product tree walked back down, 1/d per slot, the additions.
+// Hybrid: the last `aff_tail` (4) halvings are not rounds -- a thread sums the <= ~16 points its bucket still has with
+// mixed XYZZ additions (k_aff_left_list), a block the few buckets with more than 32 left (k_aff_left_sum).
+//
+// Measured on a B200 (profiles/r02q_affine_stage.md): prove() at n = 2^16 43.5 ms against 48.9 ms
+// with the XYZZ kernel, a 2^24-point MSM 74.4 against 81.6 ms; a rank of eight (15 M entries) 8.3 against 8.0 ms, hence
+// the threshold.  The additions run at 68-76 % of the multiplier pipe, the first round's denominator pass at 46 %
+// (bound by its gathers).
 #include <algorithm>
 #include <cmath>
 
