@@ -252,7 +252,8 @@ int sonic_pcv_fold(uint64_t k, const uint8_t* F48, const uint8_t* W48, const uin
  * "shard_min_terms": a standalone MSM is cut across the devices when it has at least this many terms per device (default 2^17);
  * "g2" (0/1): SRS.new also generates the G2 vectors; "sort_mode" (0: thread per term with global
  * atomics, 1: tiled counting sort with shared-memory histograms [default], 2..64: tiled with that
- * many tiles per SM);
+ * many tiles per SM); "sort_reserve" (1 default: a tile takes its slots of a bucket from the bucket's cursor by an atomic
+ * add -- the order of tiles inside a bucket is the order of arrival; 0: a prefix pass over the tile histograms fixes it);
  * "acc_mode": the bucket stage -- 3 (default) automatic: pairwise rounds in affine coordinates with batched inversions
  * when the batch has at least 5*2^22 bucket entries, the XYZZ chunk kernel below; 2 affine always; 1 XYZZ, operands in
  * shared memory; 0 XYZZ, operands in registers.  Every mode returns the same bytes.  "aff_tail" (0..5, default 4): the

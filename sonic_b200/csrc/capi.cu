@@ -1595,6 +1595,9 @@ int sonic_set_option(const char* name, int64_t value) {
         // 0: thread per term + global atomics; 1: tiled counting sort, automatic tile count; 2..64: tiled, that many tiles per SM
         if (value < 0 || value > 64) return fail(SONIC_ERR_INVALID_ARG, "sort_mode must be in [0, 64]");
         each([&](Ctx& cx) { cx.opt_sort_mode = (int)value; });
+    } else if (!strcmp(name, "sort_reserve")) {
+        if (value < 0 || value > 1) return fail(SONIC_ERR_INVALID_ARG, "sort_reserve must be 0 or 1");
+        each([&](Ctx& cx) { cx.opt_sort_reserve = (int)value; });
     } else if (!strcmp(name, "reduce_k")) {
         if (value < 0 || value > 256) return fail(SONIC_ERR_INVALID_ARG, "reduce_k must be in [0, 256]");
         each([&](Ctx& cx) { cx.opt_reduce_k = (int)value; });

@@ -127,6 +127,7 @@ struct Ctx {
     int opt_acc_mode = 3;                                 // 0 XYZZ, straight-line mixed addition in registers; 1 XYZZ compact (operand file in shared memory); 2 affine with batched inversions; 3 automatic (2 for >= 2^25 entries, else 1)
     bool opt_g2 = false;                                  // SRS.new also generates the G2 h-vectors
     int opt_reduce_mode = 0;                              // 0 automatic (quads of lanes while latency-bound, else thread per K buckets), 1 level by level, 2 thread per K buckets, 3 quads
+    int opt_sort_reserve = 1;                             // tiled sort: 1 = tiles reserve their slots of a bucket from a shared cursor (no tile-prefix pass)
     int opt_sort_mode = 1;                                // 0 thread per term + global atomics, 1 tiled counting sort (shared-memory histograms)
     bool sort_smem_set = false;
     int opt_reduce_k = 0;                                 // buckets per thread in the flat reduction (0 = automatic)

@@ -122,7 +122,8 @@ template <bool SCATTER>
 __global__ void __launch_bounds__(SORT_THREADS)
 k_msm_sort_tiles(const uint32_t* __restrict__ scalars, MsmJobTable tab, MsmTileTable tt, int c, int W, uint32_t B,
                  uint32_t level_stride,  // 0: one bucket set per window (blockIdx.y = window)
-                 uint32_t* __restrict__ hist_g, const uint32_t* __restrict__ offsets, uint32_t* __restrict__ entries) {
+                 uint32_t* __restrict__ hist_g, const uint32_t* __restrict__ offsets, uint32_t* __restrict__ entries,
+                 uint32_t* __restrict__ reserve) {   // non-null: bucket totals (COUNT) / bucket cursors (SCATTER) shared by all tiles
     extern __shared__ uint32_t hist[];
     const uint32_t tile = blockIdx.x, set = blockIdx.y, sets = gridDim.y;
     int j = 0;
@@ -131,8 +132,18 @@ k_msm_sort_tiles(const uint32_t* __restrict__ scalars, MsmJobTable tab, MsmTileT
     const uint32_t nj = tab.job[j].n;
     const uint32_t cnt = nj - first < tt.tile_terms ? nj - first : tt.tile_terms;
     uint32_t* g = hist_g + ((size_t)tile * sets + set) * B;
-    const uint32_t* off = SCATTER ? offsets + ((size_t)j * sets + set) * B : nullptr;
-    for (uint32_t b = threadIdx.x; b < B; b += SORT_THREADS) hist[b] = SCATTER ? g[b] + off[b] : 0u;
+    const uint32_t* off = SCATTER && !reserve ? offsets + ((size_t)j * sets + set) * B : nullptr;
+    uint32_t* res = reserve ? reserve + ((size_t)j * sets + set) * B : nullptr;
+    if (SCATTER && res) {
+        // the tile takes its slots of every bucket from the bucket's cursor: which tile comes first inside a bucket is
+        // left to the order of arrival (a sum does not care)
+        for (uint32_t b = threadIdx.x; b < B; b += SORT_THREADS) {
+            const uint32_t h = g[b];
+            hist[b] = h ? atomicAdd(&res[b], h) : 0u;
+        }
+    } else {
+        for (uint32_t b = threadIdx.x; b < B; b += SORT_THREADS) hist[b] = SCATTER ? g[b] + off[b] : 0u;
+    }
     __syncthreads();
     const uint4* sp = reinterpret_cast<const uint4*>(scalars + (size_t)(tab.job[j].scalar_off + first) * 8);
     const uint32_t pid0 = tab.job[j].point_base + first;
@@ -163,7 +174,11 @@ k_msm_sort_tiles(const uint32_t* __restrict__ scalars, MsmJobTable tab, MsmTileT
     }
     if (!SCATTER) {
         __syncthreads();
-        for (uint32_t b = threadIdx.x; b < B; b += SORT_THREADS) g[b] = hist[b];
+        for (uint32_t b = threadIdx.x; b < B; b += SORT_THREADS) {
+            const uint32_t h = hist[b];
+            g[b] = h;
+            if (res && h) atomicAdd(&res[b], h);
+        }
     }
 }
 
@@ -370,10 +385,21 @@ void msm_run(Ctx& cx, const G1Affine* d_points, const MsmTables& tables, const u
         }
         uint32_t* hist = ar.get<uint32_t>(hist_len);
         const dim3 grid(tiles, (unsigned)p.sets);
-        SONIC_LAUNCH(k_msm_sort_tiles<false>, grid, SORT_THREADS, sort_smem, d_scalars, tab, tt, p.c, p.W, p.B, level_stride, hist, (const uint32_t*)nullptr, (uint32_t*)nullptr);
-        SONIC_LAUNCH(k_msm_tile_prefix, div_up((uint64_t)p.GB + 1, 256), 256, 0, hist, tt, (uint32_t)p.sets * p.B, p.GB, offsets);
-        exclusive_scan_u32(ar, offsets, offsets, p.GB + 1);
-        SONIC_LAUNCH(k_msm_sort_tiles<true>, grid, SORT_THREADS, sort_smem, d_scalars, tab, tt, p.c, p.W, p.B, level_stride, hist, offsets, entries);
+        if (cx.opt_sort_reserve) {
+            // bucket totals by atomic adds of the tiles' counts; after the scan every tile reserves its slots of a bucket
+            // from the bucket's cursor (no pass over the tile histograms in between: k_msm_tile_prefix was 0.33 ms)
+            uint32_t* cursors = ar.get<uint32_t>((size_t)p.GB + 1);
+            SONIC_CUDA(cudaMemsetAsync(offsets, 0, ((size_t)p.GB + 1) * 4, st));
+            SONIC_LAUNCH(k_msm_sort_tiles<false>, grid, SORT_THREADS, sort_smem, d_scalars, tab, tt, p.c, p.W, p.B, level_stride, hist, (const uint32_t*)nullptr, (uint32_t*)nullptr, offsets);
+            exclusive_scan_u32(ar, offsets, offsets, p.GB + 1);
+            SONIC_CUDA(cudaMemcpyAsync(cursors, offsets, ((size_t)p.GB + 1) * 4, cudaMemcpyDeviceToDevice, st));
+            SONIC_LAUNCH(k_msm_sort_tiles<true>, grid, SORT_THREADS, sort_smem, d_scalars, tab, tt, p.c, p.W, p.B, level_stride, hist, (const uint32_t*)nullptr, entries, cursors);
+        } else {
+            SONIC_LAUNCH(k_msm_sort_tiles<false>, grid, SORT_THREADS, sort_smem, d_scalars, tab, tt, p.c, p.W, p.B, level_stride, hist, (const uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr);
+            SONIC_LAUNCH(k_msm_tile_prefix, div_up((uint64_t)p.GB + 1, 256), 256, 0, hist, tt, (uint32_t)p.sets * p.B, p.GB, offsets);
+            exclusive_scan_u32(ar, offsets, offsets, p.GB + 1);
+            SONIC_LAUNCH(k_msm_sort_tiles<true>, grid, SORT_THREADS, sort_smem, d_scalars, tab, tt, p.c, p.W, p.B, level_stride, hist, offsets, entries, (uint32_t*)nullptr);
+        }
     } else {
         uint32_t* cursors = ar.get<uint32_t>((size_t)p.GB + 1);
         SONIC_CUDA(cudaMemsetAsync(offsets, 0, ((size_t)p.GB + 1) * 4, st));

@@ -68,7 +68,7 @@ def test_msm_result_independent_of_tuning_options(gpu, big_srs):
             # affine coordinates with batched inversions (split and fused forms)
             gpu.set_option("window_bits", 0)
             gpu.set_option("chunk", 0)
-            for name, values in (("reduce_mode", (1, 2, 3, 0)), ("heavy_mode", (0, 1)), ("acc_mode", (0, 2)), ("aff_fused", (1, 2, 0)), ("aff_tail", (0, 2, 4)), ("aff_m", (8, 32, 64, 0)), ("acc_mode", (1, 3))):
+            for name, values in (("sort_reserve", (0, 1)), ("reduce_mode", (1, 2, 3, 0)), ("heavy_mode", (0, 1)), ("acc_mode", (0, 2)), ("aff_fused", (1, 2, 0)), ("aff_tail", (0, 2, 4)), ("aff_m", (8, 32, 64, 0)), ("acc_mode", (1, 3))):
                 for v in values:
                     gpu.set_option(name, v)
                     results.add(gpu.msm(srs, 0, -(N // 2), sc))
@@ -77,6 +77,7 @@ def test_msm_result_independent_of_tuning_options(gpu, big_srs):
         gpu.set_option("precompute", -1)
         gpu.set_option("window_bits", 0)
         gpu.set_option("chunk", 0)
+        gpu.set_option("sort_reserve", 1)
         gpu.set_option("reduce_mode", 0)
         gpu.set_option("heavy_mode", 1)
         gpu.set_option("acc_mode", 3)
