@@ -96,12 +96,12 @@ constexpr int OPEN_TILE = OPEN_THREADS * OPEN_ITEMS;
 __global__ void __launch_bounds__(OPEN_THREADS) k_open_partial(const OpenJob* __restrict__ jobs, Fr* __restrict__ partial, uint32_t tiles_stride) {
     __shared__ Fr smem[OPEN_THREADS / 32];
     const OpenJob jb = jobs[blockIdx.y];
-    const uint32_t base = blockIdx.x * OPEN_TILE + threadIdx.x * OPEN_ITEMS;
     if (blockIdx.x * OPEN_TILE >= jb.len) return;
     Fr s = Fr::zero();
+    // consecutive lanes read consecutive coefficients (the order of a sum is free)
 #pragma unroll
     for (int i = 0; i < OPEN_ITEMS; ++i) {
-        const uint32_t k = base + i;
+        const uint32_t k = blockIdx.x * OPEN_TILE + i * OPEN_THREADS + threadIdx.x;
         if (k < jb.len) s = fp_add(s, fp_mul(jb.f[k], jb.pz[k]));
     }
     s = block_sum_fr<OPEN_THREADS>(s, smem);
@@ -171,16 +171,25 @@ __global__ void __launch_bounds__(OPEN_THREADS) k_open_quotient(const OpenJob* _
     }
     const Fr H = Hin[blockIdx.y];
     const uint32_t c = (uint32_t)(-jb.lo);
-    Fr h[OPEN_ITEMS];
+    // the products h_k with consecutive lanes on consecutive coefficients (whole sectors per warp; a thread reading its
+    // four consecutive 32-byte values itself made every load touch 32 lines), handed over through shared memory to the
+    // thread that owns four consecutive slots of the scan; the scaled sums go back the same way for the stores
+    __shared__ Fr stage[OPEN_TILE];
+    const uint32_t tile0 = blockIdx.x * OPEN_TILE;
 #pragma unroll
     for (int i = 0; i < OPEN_ITEMS; ++i) {
-        const uint32_t k = base + i;
-        h[i] = Fr::zero();
+        const uint32_t j = i * OPEN_THREADS + threadIdx.x, k = tile0 + j;
+        Fr v = Fr::zero();
         if (k < jb.len) {
-            h[i] = fp_mul(jb.f[k], jb.pz[k]);
-            if (k == c) h[i] = fp_sub(h[i], H);
+            v = fp_mul(jb.f[k], jb.pz[k]);
+            if (k == c) v = fp_sub(v, H);
         }
+        stage[j] = v;
     }
+    __syncthreads();
+    Fr h[OPEN_ITEMS];
+#pragma unroll
+    for (int i = 0; i < OPEN_ITEMS; ++i) h[i] = stage[threadIdx.x * OPEN_ITEMS + i];
     // thread-local inclusive suffix
 #pragma unroll
     for (int i = OPEN_ITEMS - 2; i >= 0; --i) h[i] = fp_add(h[i], h[i + 1]);
@@ -197,13 +206,14 @@ __global__ void __launch_bounds__(OPEN_THREADS) k_open_quotient(const OpenJob* _
     Fr off = partial[(size_t)blockIdx.y * tiles_stride + blockIdx.x];
     for (int w = OPEN_THREADS / 32 - 1; w > wid; --w) off = fp_add(off, wsum[w]);
     off = fp_add(off, fp_sub(inc, h[0]));  // lanes above in this warp
+    __syncthreads();   // every thread has taken its products out of the staging buffer
+#pragma unroll
+    for (int i = 0; i < OPEN_ITEMS; ++i) stage[threadIdx.x * OPEN_ITEMS + i] = fp_add(h[i], off);
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < OPEN_ITEMS; ++i) {
-        const uint32_t k = base + i;
-        if (k >= 1 && k < jb.len) {
-            Fr S = fp_add(h[i], off);
-            jb.q_canon[k - 1] = fp_from_mont(fp_mul(S, jb.pzi[k]));
-        }
+        const uint32_t j = i * OPEN_THREADS + threadIdx.x, k = tile0 + j;
+        if (k >= 1 && k < jb.len) jb.q_canon[k - 1] = fp_from_mont(fp_mul(stage[j], jb.pzi[k]));
     }
 }
 
