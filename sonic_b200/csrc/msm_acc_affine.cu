@@ -128,6 +128,20 @@ SONIC_D Fq aff_load_y(const uint32_t* __restrict__ entries, const G1Affine* __re
 // with x = 0 does not exist ((0, +-2) has order 3), so x == 0 identifies the infinity marker (0,0).
 enum { AK_COPY = 0, AK_TAKE2, AK_INF, AK_DBL, AK_ADD };
 template <bool FIRST>
+SONIC_D int aff_kind_x(const uint32_t* __restrict__ entries, const G1Affine* __restrict__ pts, const AffSlot& sl, const Fq& x1, const Fq& x2, Fq& d) {
+    d = Fq::one();
+    if (!sl.has2) return AK_COPY;
+    if (x2.is_zero()) return AK_COPY;     // P1 + inf
+    if (x1.is_zero()) return AK_TAKE2;    // inf + P2
+    if (x1 == x2) {
+        const Fq y1 = aff_load_y<FIRST>(entries, pts, sl.i0), y2 = aff_load_y<FIRST>(entries, pts, sl.i0 + 1);
+        if (y1 == y2 && !y1.is_zero()) { d = fp_dbl(y1); return AK_DBL; }
+        return AK_INF;                    // P - P
+    }
+    d = fp_sub(x2, x1);
+    return AK_ADD;
+}
+template <bool FIRST>
 SONIC_D int aff_kind(const uint32_t* __restrict__ entries, const G1Affine* __restrict__ pts, const AffSlot& sl, const Fq& x1, Fq& d) {
     d = Fq::one();
     if (!sl.has2) return AK_COPY;
@@ -156,15 +170,28 @@ k_aff_prefix(const uint32_t* __restrict__ entries, const G1Affine* __restrict__ 
     Fq run = Fq::one();
     if (s0 < total) {
         uint32_t b = aff_find_bucket(wo, GB, s0);
+        // the x coordinates of slot j + 1 are loaded before the product of slot j: one thread walks its slots alone, and
+        // without this its loads and its products alternate
+        AffSlot sl = aff_slot(s0, b, wo, base, cnt, GB);
+        Fq x1 = aff_load_x<FIRST>(entries, pts, sl.i0);
+        Fq x2 = sl.has2 ? aff_load_x<FIRST>(entries, pts, sl.i0 + 1) : Fq::zero();
         for (int j = 0; j < AF_M; ++j) {
             const uint32_t s = s0 + j;
             if (s >= total) break;
-            const AffSlot sl = aff_slot(s, b, wo, base, cnt, GB);
-            const Fq x1 = aff_load_x<FIRST>(entries, pts, sl.i0);
+            AffSlot nsl = sl;
+            Fq nx1 = x1, nx2 = x2;
+            if (j + 1 < AF_M && s + 1 < total) {
+                nsl = aff_slot(s + 1, b, wo, base, cnt, GB);
+                nx1 = aff_load_x<FIRST>(entries, pts, nsl.i0);
+                nx2 = nsl.has2 ? aff_load_x<FIRST>(entries, pts, nsl.i0 + 1) : Fq::zero();
+            }
             Fq d;
-            aff_kind<FIRST>(entries, pts, sl, x1, d);
+            aff_kind_x<FIRST>(entries, pts, sl, x1, x2, d);
             run = fp_mul(run, d);
             pre[s] = run;
+            sl = nsl;
+            x1 = nx1;
+            x2 = nx2;
         }
     }
     // product of the block's thread totals
