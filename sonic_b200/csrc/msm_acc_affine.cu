@@ -16,7 +16,7 @@
 // Hybrid: the last `aff_tail` (4) halvings are not rounds -- a thread sums the <= ~16 points its bucket still has with
 // mixed XYZZ additions (k_aff_left_list), a block the few buckets with more than 32 left (k_aff_left_sum).
 //
-// Measured on a B200 (profiles/r02q_affine_stage.md): prove() at n = 2^16 43.5 ms against 48.9 ms
+// Measured on a B200 (profiles/r02q_affine_stage.md, r02t_bench_n1.json): prove() at n = 2^16 42.2 ms against 48.3 ms
 // with the XYZZ kernel, a 2^24-point MSM 74.4 against 81.6 ms; a rank of eight (15 M entries) 8.3 against 8.0 ms, hence
 // the threshold.  The additions run at 68-76 % of the multiplier pipe, the first round's denominator pass at 46 %
 // (bound by its gathers).
