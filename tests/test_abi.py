@@ -180,3 +180,16 @@ def test_header_compiles_as_strict_c11_and_the_consumer_links():
     if not torch.cuda.is_available():
         out = subprocess.run([os.path.join(cdir, "abi_multi"), "1", "4"], capture_output=True, text=True)
         assert out.returncode == 2 and "no CPU fallback" in out.stderr
+
+
+def test_header_documents_every_option_the_library_accepts():
+    """sonic_set_option's names live in capi.cu; the header comment is the only documentation a binding author sees."""
+    import re
+    src = open(os.path.join(ROOT, "sonic_b200", "csrc", "capi.cu")).read()
+    header = open(os.path.join(ROOT, "include", "sonic_b200.h")).read()
+    body = src[src.index("int sonic_set_option("):]
+    body = body[:body.index("\n}\n")]
+    names = sorted(set(re.findall(r'!strcmp\(name, "([a-z_0-9]+)"\)', body)))
+    assert len(names) >= 15, names
+    missing = [n for n in names if '"%s"' % n not in header]
+    assert not missing, "options accepted by sonic_set_option but absent from include/sonic_b200.h: %s" % missing
